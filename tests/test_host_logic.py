@@ -1,0 +1,156 @@
+"""Host logic (tool parser, task planner, model loaders) against golden vectors produced by the
+real reference code (tests/golden/make_host_golden.py imports /root/reference/remo3d/remo3d.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from remo3d_b200 import model_io, planner, tools as tl
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    with open(os.path.join(golden_dir, "host_golden.json")) as f:
+        return json.load(f)
+
+
+def _arr(x):
+    return np.array([[np.nan if v == "nan" else v for v in row] for row in x], dtype=float)
+
+
+def test_tool_parameters_bit_exact(gold):
+    for key, g in gold["tools"].items():
+        names, fsec = key.split("|")
+        names = names.split(",")
+        params, sec = tl.set_tools_parameters(names, fsec == "True")
+        assert sec == g["sec"]
+        assert list(params.keys()) == names
+        for t in names:
+            np.testing.assert_array_equal(params[t], np.array(g["params"][t]), err_msg=t)
+
+
+def test_tool_table_survey_values():
+    # SURVEY.md §3.4 worked values
+    p, sec = tl.set_tools_parameters(["B5.7A0.4M", "N0.5M2.0A", "M4.0A0.5B"])
+    assert sec
+    np.testing.assert_allclose(p["B5.7A0.4M"], [[-6.1, -0.4, 0, 5.37929], [0, 0, 1, 0.2]], atol=1e-5)
+    np.testing.assert_allclose(p["N0.5M2.0A"], [[-2.5, -2.0, 0, 125.66371], [0, 0, 1, 2.25]], atol=1e-5)
+    np.testing.assert_allclose(p["M4.0A0.5B"], [[0, 4.0, 4.5, 452.38934], [1, 0, 0, -4.25]], atol=1e-5)
+
+
+def test_tool_errors(gold):
+    for name, msg in gold["tool_errors"].items():
+        if name.startswith("'") or name.startswith("["):
+            arg = eval(name)
+        else:
+            arg = [name]
+        if msg is None:
+            tl.set_tools_parameters(arg)
+        else:
+            with pytest.raises(ValueError) as e:
+                tl.set_tools_parameters(arg)
+            assert str(e.value) == msg
+    with pytest.raises(ValueError):
+        tl.set_tools_parameters(["A1.0M2.0N"], force_single_electrode_configuration=1)
+
+
+def _cmp_nested(a, b, path="task"):
+    """Compare our task nesting with the golden (lists / arrays / scalars; 'nan' strings)."""
+    if isinstance(b, list):
+        a_list = a.tolist() if isinstance(a, np.ndarray) else a
+        assert len(a_list) == len(b), path
+        for i, (x, y) in enumerate(zip(a_list, b)):
+            _cmp_nested(x, y, "%s[%d]" % (path, i))
+    elif b == "nan":
+        assert a != a, path
+    else:
+        assert a == b, "%s: %r != %r" % (path, a, b)
+
+
+def test_planner_bit_exact(gold):
+    for g in gold["planner"]:
+        params, sec = tl.set_tools_parameters(g["tools"], g["fsec"])
+        centres, tasks = planner.prepare_simulation_depths_and_tasks(params, sec, np.array(g["depths"]), g["batch_size"])
+        _cmp_nested(centres, g["combined_depths"], "centres")
+        _cmp_nested(tasks, g["tasks"])
+
+
+def test_planner_example01_counts():
+    # 6 tools x 251 depths, sec mode: 1506 log values <- 818 solves <- 164 meshes
+    names = ["B5.7A0.4M", "B4.48A1.62M", "M1.0A0.1B", "A2.0M0.5N", "N0.5M2.0A", "M4.0A0.5B"]
+    params, sec = tl.set_tools_parameters(names)
+    _, tasks = planner.prepare_simulation_depths_and_tasks(params, sec, np.arange(0, 25.1, 0.1), 5)
+    assert len(tasks) == 164
+    assert sum(len(t[2]) for t in tasks) == 818
+    assert sum(len(s[2]) for t in tasks for s in t[2]) == 1506
+
+
+def test_flatten_task():
+    names = ["A2.0M0.5N", "N0.5M2.0A", "A0.2B3.0M"]
+    params, sec = tl.set_tools_parameters(names, False)
+    assert not sec
+    _, tasks = planner.prepare_simulation_depths_and_tasks(params, sec, np.arange(3, 4, 0.25), 4)
+    seen = 0
+    for task in tasks:
+        f = planner.flatten_task(task, params, three_d=True)
+        nrhs = len(task[2])
+        assert f["src_ptr"].shape == (nrhs + 1,)
+        assert f["scale"] == 0.5
+        for r, st in enumerate(task[2]):
+            lo, hi = f["src_ptr"][r], f["src_ptr"][r + 1]
+            el = st[1]
+            np.testing.assert_array_equal(f["src_z"][lo:hi], el[0, el[1] != 0])
+            np.testing.assert_array_equal(f["src_fac"][lo:hi], el[1, el[1] != 0])
+        for i in range(f["pt_rhs"].shape[0]):
+            p = params[names[f["pt_tool"][i]]]
+            n_pot = int(np.sum(p[1, :3] == 0))
+            assert np.isnan(f["pt_z1"][i]) == (n_pot == 1)
+            seen += 1
+    assert seen == 3 * 4
+
+
+def test_loaders(gold, tmp_path):
+    for k, g in gold["loaders"].items():
+        ff = tmp_path / (k + "_f.txt")
+        bf = tmp_path / (k + "_b.txt")
+        ff.write_text(g["formation_text"])
+        bf.write_text(g["borehole_text"])
+        f = model_io.load_formation_parameters(str(ff))
+        b = model_io.load_borehole_parameters(str(bf))
+        np.testing.assert_array_equal(f, _arr(g["formation"]))
+        np.testing.assert_array_equal(b, _arr(g["borehole"]))
+        model_io.check_model_geometry(f, b)
+
+
+def test_setter_errors(gold):
+    nan = np.nan
+    cases = {
+        "formation_gap": lambda: model_io.set_formation_parameters(np.array([[0., 1, nan, nan, 5], [1.5, 2, nan, nan, 5]])),
+        "formation_neg_res": lambda: model_io.set_formation_parameters(np.array([[0., 1, nan, nan, -5]])),
+        "formation_unit": lambda: model_io.set_formation_parameters(np.array([[0., 1, nan, nan, 5]]), ["M", "KM", "M"]),
+        "borehole_one_row": lambda: model_io.set_borehole_parameters(np.array([[0., 0.2, 1.0]])),
+        "borehole_neg": lambda: model_io.set_borehole_parameters(np.array([[0., -0.2, 1.0], [1.0, 0.2, 1.0]])),
+        "borehole_type": lambda: model_io.set_borehole_parameters(np.array([[0., 0.2, 1.0], [1.0, 0.2, 1.0]]), "circumference"),
+        "borehole_rm": lambda: model_io.set_borehole_parameters(np.array([[0., 0.2, 0.0], [1.0, 0.2, 1.0]])),
+        "borehole_unit": lambda: model_io.set_borehole_parameters(np.array([[0., 0.2, 1.0], [1.0, 0.2, 1.0]]), units=["M", "YD"]),
+        "dip_90": lambda: model_io.set_dip(90),
+        "dip_neg": lambda: model_io.set_dip(-1),
+    }
+    for k, fn in cases.items():
+        msg = gold["setter_errors"][k]
+        assert msg is not None
+        with pytest.raises(ValueError) as e:
+            fn()
+        assert str(e.value) == msg, k
+    assert list(model_io.set_dip(30)) == gold["dip_30"]
+
+
+def test_densify_borehole():
+    b = np.array([[0.0, 0.1, 1.0], [0.1, 0.1, 1.0], [1.1, 0.2, 2.0]])
+    d = model_io.densify_borehole(b)
+    assert d.shape[0] > 3 and d[0, 0] == 0.0 and d[-1, 0] == 1.1
+    assert np.all(np.diff(d[:, 0]) > 0)
+    np.testing.assert_allclose(np.interp(0.6, d[:, 0], d[:, 1]), 0.15)
+    same = model_io.densify_borehole(b[:2])
+    assert same is b[:2] or np.array_equal(same, b[:2])
