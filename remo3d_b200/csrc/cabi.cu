@@ -1,0 +1,344 @@
+// C ABI of libremo3d_b200.so (declared in include/remo3d_b200.h).  Thin: argument checks, copies and
+// the try/catch that keeps C++ exceptions from crossing the boundary.
+#include <cstring>
+
+#include "space_view.cuh"
+
+namespace {
+
+__global__ void k_gather_axis_z(const double* __restrict__ xyz, const int32_t* __restrict__ axis_v, int64_t n, int dim,
+                                double* __restrict__ z, int* __restrict__ bad, int64_t nv) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t v = axis_v[i];
+  if (v < 0 || v >= nv) { atomicExch(bad, 1); return; }
+  z[i] = xyz[(int64_t)v * dim + (dim - 1)];
+}
+
+__global__ void k_check_sorted(const double* __restrict__ z, int64_t n, int* __restrict__ bad) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i + 1 < n && !(z[i] < z[i + 1])) atomicExch(bad, 2);
+}
+
+__global__ void k_check_elems(const int32_t* __restrict__ e, int64_t n, int64_t nv, int* __restrict__ bad) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n && (e[i] < 0 || e[i] >= nv)) atomicExch(bad, 3);
+}
+
+__global__ void k_extract_col(const double* __restrict__ X, int64_t n, int k, int r, double* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = X[i * k + r];
+}
+
+template <typename F>
+int guarded(void* vctx, F&& f) {
+  Ctx* c = static_cast<Ctx*>(vctx);
+  if (!c) return REMO_ERR_ARG;
+  try {
+    CK(cudaSetDevice(c->device));
+    return f(c);
+  } catch (const RemoError& e) {
+    c->err = e.msg;
+    return e.code;
+  } catch (const std::exception& e) {
+    c->err = e.what();
+    return REMO_ERR_CUDA;
+  } catch (...) {
+    c->err = "unknown error";
+    return REMO_ERR_CUDA;
+  }
+}
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+extern "C" {
+
+int remo_ctx_create(int device, void** out) {
+  if (!out) return REMO_ERR_ARG;
+  *out = nullptr;
+  Ctx* c = nullptr;
+  try {
+    int count = 0;
+    CK(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) FAIL(REMO_ERR_ARG, "remo_ctx_create: device %d not available (%d CUDA devices)", device, count);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) FAIL(REMO_ERR_CUDA, "remo_ctx_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    c = new Ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;  // keep freed blocks in the pool: per-mesh reallocation stays cheap
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    for (int i = 0; i < REMO_NSTAGE; i++) {
+      CK(cudaEventCreate(&c->ev0[i]));
+      CK(cudaEventCreate(&c->ev1[i]));
+    }
+    *out = c;
+    return REMO_OK;
+  } catch (const RemoError& e) {
+    g_create_error = e.msg;
+    delete c;
+    return e.code;
+  }
+}
+
+int remo_ctx_destroy(void* vctx) {
+  Ctx* c = static_cast<Ctx*>(vctx);
+  if (!c) return REMO_ERR_ARG;
+  cudaSetDevice(c->device);
+  cudaStream_t s = c->stream;
+  cudaStreamSynchronize(s);
+  c->xyz.release(s); c->elems.release(s); c->mat.release(s); c->bfacets.release(s); c->bdir.release(s);
+  c->axis_v.release(s); c->axis_z.release(s); c->sv.release(s); c->edge_keys.release(s); c->elem_edges.release(s);
+  c->face_keys.release(s); c->elem_faces.release(s); c->constrained.release(s); c->adj_ptr.release(s); c->adj.release(s);
+  c->rowptr.release(s); c->col.release(s); c->val.release(s); c->gm.release(s); c->sigma.release(s); c->rvert.release(s);
+  c->dinv.release(s); c->c_rowptr.release(s); c->c_col.release(s); c->c_val.release(s); c->c_dinv.release(s);
+  c->cw0.release(s); c->cw1.release(s); c->cw2.release(s);
+  c->F.release(s); c->X.release(s); c->R.release(s); c->Z.release(s); c->P.release(s); c->Q.release(s);
+  c->partial.release(s); c->scal.release(s); c->iters_d.release(s); c->tmp.release(s);
+  cudaStreamSynchronize(s);
+  for (int i = 0; i < REMO_NSTAGE; i++) { cudaEventDestroy(c->ev0[i]); cudaEventDestroy(c->ev1[i]); }
+  for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+  cudaStreamDestroy(s);
+  delete c;
+  return REMO_OK;
+}
+
+const char* remo_last_error(void* vctx) {
+  Ctx* c = static_cast<Ctx*>(vctx);
+  return c ? c->err.c_str() : g_create_error.c_str();
+}
+
+int remo_mesh_set(void* vctx, int dim, int64_t nv, const double* xyz, int64_t nt, const int32_t* elems, const int32_t* mat,
+                  int64_t nb, const int32_t* bfacets, const uint8_t* bdirichlet, int64_t naxis, const int32_t* axis_vertices) {
+  return guarded(vctx, [&](Ctx* c) {
+    if (dim != 2 && dim != 3) FAIL(REMO_ERR_ARG, "remo_mesh_set: dim must be 2 or 3 (got %d)", dim);
+    if (nv < dim + 1 || nt < 1 || !xyz || !elems || !mat) FAIL(REMO_ERR_ARG, "remo_mesh_set: empty mesh");
+    if (nv >= (int64_t)1 << 31) FAIL(REMO_ERR_ARG, "remo_mesh_set: too many vertices");
+    if (nb < 0 || (nb > 0 && (!bfacets || !bdirichlet))) FAIL(REMO_ERR_ARG, "remo_mesh_set: boundary arrays missing");
+    if (naxis < 0 || (naxis > 0 && !axis_vertices)) FAIL(REMO_ERR_ARG, "remo_mesh_set: axis array missing");
+    StageTimer timer(c, ST_MESH);
+    cudaStream_t st = c->stream;
+    c->have_mesh = c->have_space = c->have_matrix = c->have_rhs = c->have_solution = false;
+    c->pkind = -1;
+    c->dim = dim; c->nv = nv; c->nt = nt; c->nb = nb; c->naxis = naxis;
+    c->xyz.ensure(nv * dim, st); c->elems.ensure(nt * (dim + 1), st); c->mat.ensure(nt, st);
+    c->bfacets.ensure(std::max<int64_t>(nb * dim, 1), st); c->bdir.ensure(std::max<int64_t>(nb, 1), st);
+    c->axis_v.ensure(std::max<int64_t>(naxis, 1), st); c->axis_z.ensure(std::max<int64_t>(naxis, 1), st);
+    CK(cudaMemcpyAsync(c->xyz.p, xyz, nv * dim * sizeof(double), cudaMemcpyDefault, st));
+    CK(cudaMemcpyAsync(c->elems.p, elems, nt * (dim + 1) * sizeof(int32_t), cudaMemcpyDefault, st));
+    CK(cudaMemcpyAsync(c->mat.p, mat, nt * sizeof(int32_t), cudaMemcpyDefault, st));
+    if (nb) {
+      CK(cudaMemcpyAsync(c->bfacets.p, bfacets, nb * dim * sizeof(int32_t), cudaMemcpyDefault, st));
+      CK(cudaMemcpyAsync(c->bdir.p, bdirichlet, nb, cudaMemcpyDefault, st));
+    }
+    DBuf<int> bad;
+    bad.ensure(1, st);
+    CK(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+    LAUNCH(c, k_check_elems, grid_for(nt * (dim + 1), 256), 256, 0, c->elems.p, nt * (dim + 1), nv, bad.p);
+    if (nb) LAUNCH(c, k_check_elems, grid_for(nb * dim, 256), 256, 0, c->bfacets.p, nb * dim, nv, bad.p);
+    if (naxis) {
+      CK(cudaMemcpyAsync(c->axis_v.p, axis_vertices, naxis * sizeof(int32_t), cudaMemcpyDefault, st));
+      LAUNCH(c, k_gather_axis_z, grid_for(naxis, 256), 256, 0, c->xyz.p, c->axis_v.p, naxis, dim, c->axis_z.p, bad.p, nv);
+      LAUNCH(c, k_check_sorted, grid_for(naxis, 256), 256, 0, c->axis_z.p, naxis, bad.p);
+    }
+    int h = 0;
+    CK(cudaMemcpyAsync(&h, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    bad.release(st);
+    if (h == 1) FAIL(REMO_ERR_MESH, "remo_mesh_set: axis vertex number out of range");
+    if (h == 2) FAIL(REMO_ERR_MESH, "remo_mesh_set: axis vertices are not strictly ascending in z");
+    if (h == 3) FAIL(REMO_ERR_MESH, "remo_mesh_set: element or boundary facet refers to a vertex outside 0..nv-1");
+    c->have_mesh = true;
+    return REMO_OK;
+  });
+}
+
+int remo_space_build(void* vctx, int order, int64_t* ndof, int64_t* nnz, int64_t* nedges, int64_t* nfaces) {
+  return guarded(vctx, [&](Ctx* c) {
+    space_build(c, order);
+    if (ndof) *ndof = c->ndof;
+    if (nnz) *nnz = c->nnz;
+    if (nedges) *nedges = c->ne;
+    if (nfaces) *nfaces = c->nf;
+    return REMO_OK;
+  });
+}
+
+int remo_topology_get(void* vctx, int32_t* edges, int32_t* faces, int32_t* elem_edges, int32_t* elem_faces) {
+  return guarded(vctx, [&](Ctx* c) {
+    topology_get(c, edges, faces, elem_edges, elem_faces);
+    return REMO_OK;
+  });
+}
+
+int remo_assemble(void* vctx, int nmat, const double* sigma) {
+  return guarded(vctx, [&](Ctx* c) {
+    assemble(c, nmat, sigma);
+    return REMO_OK;
+  });
+}
+
+int remo_matrix_get(void* vctx, int64_t* rowptr, int32_t* col, double* val) {
+  return guarded(vctx, [&](Ctx* c) {
+    if (!c->have_space) FAIL(REMO_ERR_STATE, "remo_matrix_get: no space");
+    if (val && !c->have_matrix) FAIL(REMO_ERR_STATE, "remo_matrix_get: matrix not assembled");
+    cudaStream_t st = c->stream;
+    if (rowptr) CK(cudaMemcpyAsync(rowptr, c->rowptr.p, (c->ndof + 1) * sizeof(int64_t), cudaMemcpyDefault, st));
+    if (col) CK(cudaMemcpyAsync(col, c->col.p, c->nnz * sizeof(int32_t), cudaMemcpyDefault, st));
+    if (val) CK(cudaMemcpyAsync(val, c->val.p, c->nnz * sizeof(double), cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
+    return REMO_OK;
+  });
+}
+
+int remo_dirichlet_get(void* vctx, uint8_t* constrained) {
+  return guarded(vctx, [&](Ctx* c) {
+    if (!c->have_space || !constrained) FAIL(REMO_ERR_STATE, "remo_dirichlet_get: no space");
+    CK(cudaMemcpyAsync(constrained, c->constrained.p, c->ndof, cudaMemcpyDefault, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return REMO_OK;
+  });
+}
+
+int remo_precond_setup(void* vctx, int kind) {
+  return guarded(vctx, [&](Ctx* c) {
+    precond_setup(c, kind);
+    return REMO_OK;
+  });
+}
+
+int remo_rhs_point_sources(void* vctx, int nrhs, const int64_t* src_ptr, const double* src_z, const double* src_fac) {
+  return guarded(vctx, [&](Ctx* c) {
+    if (!src_ptr) FAIL(REMO_ERR_ARG, "remo_rhs_point_sources: src_ptr is NULL");
+    rhs_point_sources(c, nrhs, src_ptr, src_z, src_fac);
+    return REMO_OK;
+  });
+}
+
+static int get_column(Ctx* c, const double* block, int rhs, double* out, const char* who) {
+  if (rhs < 0 || rhs >= c->nrhs || !out) FAIL(REMO_ERR_ARG, "%s: right-hand-side index out of range", who);
+  DBuf<double> t;
+  t.ensure(c->ndof, c->stream);
+  LAUNCH(c, k_extract_col, grid_for(c->ndof, 256), 256, 0, block, c->ndof, c->nrhs, rhs, t.p);
+  CK(cudaMemcpyAsync(out, t.p, c->ndof * sizeof(double), cudaMemcpyDefault, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  t.release(c->stream);
+  return REMO_OK;
+}
+
+int remo_rhs_get(void* vctx, int rhs, double* f) {
+  return guarded(vctx, [&](Ctx* c) {
+    if (!c->have_rhs) FAIL(REMO_ERR_STATE, "remo_rhs_get: no right-hand side");
+    return get_column(c, c->F.p, rhs, f, "remo_rhs_get");
+  });
+}
+
+int remo_solve(void* vctx, double rtol, int maxit, int* iters, double* relres) {
+  return guarded(vctx, [&](Ctx* c) { return solve(c, rtol, maxit, iters, relres); });
+}
+
+int remo_sample_axis(void* vctx, int npts, const int32_t* pt_rhs, const double* z, double* u_out) {
+  return guarded(vctx, [&](Ctx* c) {
+    if (npts > 0 && (!z || !u_out)) FAIL(REMO_ERR_ARG, "remo_sample_axis: NULL buffer");
+    sample_axis(c, npts, pt_rhs, z, u_out);
+    return REMO_OK;
+  });
+}
+
+int remo_apparent_resistivity(void* vctx, int npts, const int32_t* pt_rhs, const double* z0, const double* z1, const double* k,
+                              double scale, double* ra) {
+  return guarded(vctx, [&](Ctx* c) {
+    if (npts > 0 && (!pt_rhs || !z0 || !z1 || !k || !ra)) FAIL(REMO_ERR_ARG, "remo_apparent_resistivity: NULL buffer");
+    apparent_resistivity(c, npts, pt_rhs, z0, z1, k, scale, ra);
+    return REMO_OK;
+  });
+}
+
+int remo_solution_get(void* vctx, int rhs, double* u) {
+  return guarded(vctx, [&](Ctx* c) {
+    if (!c->have_solution) FAIL(REMO_ERR_STATE, "remo_solution_get: no solution");
+    return get_column(c, c->X.p, rhs, u, "remo_solution_get");
+  });
+}
+
+int remo_kernel_time(void* vctx, int which, int nrhs, int reps, float* ms) {
+  return guarded(vctx, [&](Ctx* c) {
+    if (!c->have_matrix) FAIL(REMO_ERR_STATE, "remo_kernel_time: assemble a matrix first");
+    if (reps < 1 || !ms || nrhs < 1 || nrhs > REMO_MAX_RHS) FAIL(REMO_ERR_ARG, "remo_kernel_time: bad arguments");
+    cudaStream_t st = c->stream;
+    if (which == 0 || which == 2) {
+      if (c->nrhs != nrhs || !c->have_rhs) {
+        alloc_solver_state(c, nrhs);
+        CK(cudaMemsetAsync(c->F.p, 0, (size_t)c->ndof * nrhs * sizeof(double), st));
+        c->have_rhs = true;
+        c->have_solution = false;
+      }
+      if (c->pkind < 0) precond_setup(c, REMO_PRECOND_LOCAL);
+      // deterministic non-trivial vectors: P = dinv-scaled ones pattern is not needed for timing; reuse F
+      CK(cudaMemcpyAsync(c->P.p, c->F.p, (size_t)c->ndof * nrhs * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemsetAsync(c->scal.p, 0, c->scal.n * sizeof(double), st));
+    }
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    auto body = [&]() {
+      if (which == 0) launch_spmm(c, c->P.p, c->Q.p, nrhs);
+      else if (which == 1) assemble_kernels_only(c);
+      else launch_vector_updates(c, nrhs);
+    };
+    body();  // warm-up
+    CK(cudaEventRecord(a, st));
+    for (int i = 0; i < reps; i++) body();
+    CK(cudaEventRecord(b, st));
+    CK(cudaEventSynchronize(b));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, a, b));
+    *ms = t / reps;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    return REMO_OK;
+  });
+}
+
+int remo_profile(void* vctx, int on) {
+  Ctx* c = static_cast<Ctx*>(vctx);
+  if (!c) return REMO_ERR_ARG;
+  c->prof = on != 0;
+  c->prof_spmm_ms = 0.0;
+  c->prof_spmm_n = 0;
+  return REMO_OK;
+}
+
+int remo_profile_get(void* vctx, double* spmm_ms_total, int64_t* spmm_launches) {
+  Ctx* c = static_cast<Ctx*>(vctx);
+  if (!c || !spmm_ms_total || !spmm_launches) return REMO_ERR_ARG;
+  *spmm_ms_total = c->prof_spmm_ms;
+  *spmm_launches = c->prof_spmm_n;
+  return REMO_OK;
+}
+
+int64_t remo_launch_count(void* vctx) {
+  Ctx* c = static_cast<Ctx*>(vctx);
+  return c ? c->launches : -1;
+}
+
+int remo_stage_times(void* vctx, float* ms7) {
+  return guarded(vctx, [&](Ctx* c) {
+    if (!ms7) FAIL(REMO_ERR_ARG, "remo_stage_times: NULL buffer");
+    CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < REMO_NSTAGE; i++) {
+      ms7[i] = 0.f;
+      if (c->ev_set[i]) CK(cudaEventElapsedTime(&ms7[i], c->ev0[i], c->ev1[i]));
+    }
+    return REMO_OK;
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+// Internal context of libremo3d_b200 (not part of the public ABI; see include/remo3d_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/remo3d_b200.h"
+
+#define REMO_NSTAGE 7
+enum { ST_MESH = 0, ST_SPACE, ST_ASM, ST_PRECOND, ST_RHS, ST_SOLVE, ST_SAMPLE };
+
+struct Ctx;
+
+// ---- error plumbing: every CUDA call goes through CK(), every entry point through the try/catch in cabi.cu
+struct RemoError {
+  int code;
+  std::string msg;
+};
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      char b__[512];                                                                               \
+      snprintf(b__, sizeof b__, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      throw RemoError{REMO_ERR_CUDA, b__};                                                         \
+    }                                                                                              \
+  } while (0)
+#define FAIL(code, ...)                      \
+  do {                                       \
+    char b__[512];                           \
+    snprintf(b__, sizeof b__, __VA_ARGS__);  \
+    throw RemoError{code, b__};              \
+  } while (0)
+
+// ---- stream-ordered device buffer (pool keeps freed blocks, so per-mesh re-allocation is cheap)
+template <typename T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;    // elements in use
+  size_t cap = 0;  // elements allocated
+  void ensure(size_t count, cudaStream_t s) {
+    if (count > cap) {
+      if (p) CK(cudaFreeAsync(p, s));
+      p = nullptr;
+      cap = 0;
+      size_t want = count + count / 8 + 64;
+      CK(cudaMallocAsync((void**)&p, want * sizeof(T), s));
+      cap = want;
+    }
+    n = count;
+  }
+  void release(cudaStream_t s) {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr;
+    n = cap = 0;
+  }
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  int num_sms = 148;
+  cudaEvent_t ev0[REMO_NSTAGE], ev1[REMO_NSTAGE];
+  bool ev_set[REMO_NSTAGE] = {false};
+
+  // ---- mesh (remo_mesh_set)
+  int dim = 0;
+  int64_t nv = 0, nt = 0, nb = 0, naxis = 0;
+  DBuf<double> xyz;       // nv x dim
+  DBuf<int32_t> elems;    // nt x (dim+1)
+  DBuf<int32_t> mat;      // nt
+  DBuf<int32_t> bfacets;  // nb x dim
+  DBuf<uint8_t> bdir;     // nb
+  DBuf<int32_t> axis_v;   // naxis
+  DBuf<double> axis_z;    // naxis
+  bool have_mesh = false;
+
+  // ---- space (remo_space_build)
+  int order = 0, nld = 0, nle = 0, nlf = 0, npair = 0;
+  int64_t ne = 0, nf = 0, ndof = 0, nnz = 0, nadj = 0;
+  int64_t edge_base = 0, face_base = 0;
+  DBuf<int32_t> sv;           // nt x (dim+1), vertices of every element sorted ascending
+  DBuf<uint64_t> edge_keys;   // ne   (a<<32 | b), ascending  == lexicographic edge numbering
+  DBuf<int32_t> elem_edges;   // nt x nle
+  DBuf<uint64_t> face_keys;   // nf   (edge(a,b)<<32 | c), ascending == lexicographic face numbering
+  DBuf<int32_t> elem_faces;   // nt x nlf
+  DBuf<uint8_t> constrained;  // ndof
+  DBuf<int64_t> adj_ptr;      // ndof+1: dof -> range in adj
+  DBuf<uint32_t> adj;         // nadj = nt*nld: element*nld + local dof, elements ascending per dof
+  DBuf<int64_t> rowptr;       // ndof+1
+  DBuf<int32_t> col;          // nnz, ascending per row
+  DBuf<double> val;           // nnz
+  bool have_space = false, have_matrix = false;
+
+  // ---- numeric
+  DBuf<double> gm;     // nt x npair: sigma |K| grad l_i . grad l_j
+  DBuf<double> sigma;  // nmat
+  DBuf<double> rvert;  // 2D: nt x 3 radii of the sorted vertices
+
+  // ---- preconditioner
+  int pkind = -1;
+  DBuf<double> dinv;  // ndof: 1/diag on free dofs, 0 on constrained
+  // two-level: vertex-block coarse operator
+  DBuf<int64_t> c_rowptr;
+  DBuf<int32_t> c_col;
+  DBuf<double> c_val;
+  DBuf<double> c_dinv;
+  int64_t c_nnz = 0;
+  int coarse_sweeps = 0;
+  DBuf<double> cw0, cw1, cw2;  // coarse work vectors nv x nrhs
+
+  // ---- right-hand sides / PCG state, row-major ndof x nrhs
+  int nrhs = 0;
+  DBuf<double> F, X, R, Z, P, Q;
+  DBuf<double> partial;  // per-block partial dot products
+  DBuf<double> scal;     // device scalars, see solver.cu
+  DBuf<int> iters_d;
+  bool have_rhs = false, have_solution = false;
+
+  // ---- per-launch SpMM timing inside remo_solve (remo_profile): CUDA events around every SpMM launch
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_ev;
+  double prof_spmm_ms = 0.0;
+  int64_t prof_spmm_n = 0;
+
+  // ---- scratch
+  DBuf<uint8_t> tmp;  // CUB temp storage
+  std::vector<double> host_scal;
+};
+
+// ---- launch helper: counts launches (bench.py gpu_launches) and checks the launch
+#define LAUNCH(ctx, kern, grid, block, smem, ...)                      \
+  do {                                                                 \
+    kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);     \
+    (ctx)->launches++;                                                 \
+    CK(cudaGetLastError());                                            \
+  } while (0)
+
+static inline unsigned grid_for(int64_t n, int block, int64_t cap = (1 << 30)) {
+  int64_t g = (n + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (unsigned)g;
+}
+
+struct StageTimer {
+  Ctx* c;
+  int st;
+  StageTimer(Ctx* c_, int st_) : c(c_), st(st_) { cudaEventRecord(c->ev0[st], c->stream); }
+  ~StageTimer() {
+    cudaEventRecord(c->ev1[st], c->stream);
+    c->ev_set[st] = true;
+  }
+};
+
+// symbolic.cu
+void space_build(Ctx* c, int order);
+void topology_get(Ctx* c, int32_t* edges, int32_t* faces, int32_t* elem_edges, int32_t* elem_faces);
+// assemble.cu
+void assemble(Ctx* c, int nmat, const double* sigma);
+void assemble_kernels_only(Ctx* c);
+// solver.cu
+void precond_setup(Ctx* c, int kind);
+void rhs_point_sources(Ctx* c, int nrhs, const int64_t* src_ptr, const double* src_z, const double* src_fac);
+int solve(Ctx* c, double rtol, int maxit, int* iters, double* relres);
+void sample_axis(Ctx* c, int npts, const int32_t* pt_rhs, const double* z, double* out);
+void apparent_resistivity(Ctx* c, int npts, const int32_t* pt_rhs, const double* z0, const double* z1, const double* k,
+                          double scale, double* ra);
+void launch_spmm(Ctx* c, const double* P, double* Q, int nrhs);
+void launch_vector_updates(Ctx* c, int nrhs);
+void alloc_solver_state(Ctx* c, int nrhs);

@@ -1,0 +1,527 @@
+// Preconditioned conjugate gradients for all right-hand sides of one mesh at once, point sources,
+// axis sampling and apparent resistivity.  Replaces
+//   c = ngs.Preconditioner(a, preconditioner); inv = ngs.CGSolver(a.mat, c.mat, maxsteps=1000);
+//   gfu.vec.data = inv * f.vec                       (/root/reference/remo3d/ngsolve_functions.py:46-51,
+//                                                      device form ngsolve_functions_gpu.py:41-47)
+//   AddPointSource                                    (ngsolve_functions.py:10-21, 39-44)
+//   gfu(mesh(0.0, 0.0, z)), Ra = |K dU| / 2           (workers/worker.py:113-134)
+//
+// Data layout: every vector block (F, X, R, Z, P, Q) is row-major ndof x nrhs, so the nrhs values of one dof
+// are contiguous: the SpMM gathers one contiguous nrhs*8-byte segment per matrix entry and the matrix
+// (12 B per non-zero) is streamed once per iteration for ALL right-hand sides.
+// The columns run in lockstep with their own alpha/beta (device-resident scalars, no host round trip per
+// iteration); a converged column is frozen (alpha = beta = 0).  Dot products are reduced block-wise into a
+// partial array and finished in a fixed order by a one-block kernel -> bit-reproducible runs.
+#include "space_view.cuh"
+
+namespace {
+
+constexpr int TB = 256;
+constexpr int KMAX = REMO_MAX_RHS;  // 32
+// scalar slots (each KMAX doubles)
+enum { S_RZ = 0, S_ALPHA, S_BETA, S_RR, S_BB, S_ACTIVE, S_TOL2, S_PQ, S_NSLOT };
+
+__device__ __forceinline__ double warp_sum(double v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SpMM  Q = A P  (constrained rows -> 0) with the fused per-column dot  p.q
+// one warp per row; lane = (jsub, r): KP lanes cover the right-hand sides, 32/KP matrix entries in flight
+// ------------------------------------------------------------------------------------------------
+template <int KP>
+__global__ void __launch_bounds__(TB) k_spmm(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                             const double* __restrict__ val, const uint8_t* __restrict__ constrained,
+                                             const double* __restrict__ P, double* __restrict__ Q, int k, int64_t n,
+                                             double* __restrict__ partial) {
+  constexpr int J = 32 / KP;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int jsub = lane / KP, r = lane % KP;
+  const bool on = r < k;
+  const int64_t nwarps = (int64_t)gridDim.x * (TB / 32);
+  double dot = 0.0;
+  for (int64_t row = (int64_t)blockIdx.x * (TB / 32) + warp; row < n; row += nwarps) {
+    const int64_t s = rowptr[row], e = rowptr[row + 1];
+    double acc = 0.0;
+    for (int64_t j = s + jsub; j < e; j += J) {
+      const int32_t c = __ldg(col + j);
+      const double v = __ldg(val + j);
+      if (on) acc = fma(v, P[(int64_t)c * k + r], acc);
+    }
+#pragma unroll
+    for (int o = 16; o >= KP; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (constrained[row]) acc = 0.0;
+    if (jsub == 0 && on) {
+      Q[row * k + r] = acc;
+      dot = fma(acc, P[row * k + r], dot);
+    }
+  }
+  // block reduction of the per-column dots: lanes with equal r across the warps
+  __shared__ double sh[TB / 32][32];
+  sh[warp][lane] = (jsub == 0 && on) ? dot : 0.0;
+  __syncthreads();
+  if (warp == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < TB / 32; w++) t += sh[w][lane];
+    if (lane < KP) partial[(int64_t)blockIdx.x * KMAX + lane] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// vector kernels: thread = (row group, r) with r = threadIdx % KP
+// ------------------------------------------------------------------------------------------------
+template <int KP>
+__device__ __forceinline__ void block_partials(double a, double b, double* __restrict__ partial, int nslots) {
+  // threads with equal (threadIdx % KP) hold the same column
+  __shared__ double sh[2][TB];
+  sh[0][threadIdx.x] = a;
+  sh[1][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.x < KP) {
+    double ta = 0.0, tb = 0.0;
+    for (int i = threadIdx.x; i < TB; i += KP) { ta += sh[0][i]; tb += sh[1][i]; }
+    partial[((int64_t)blockIdx.x * 2 + 0) * KMAX + threadIdx.x] = ta;
+    if (nslots > 1) partial[((int64_t)blockIdx.x * 2 + 1) * KMAX + threadIdx.x] = tb;
+  }
+}
+
+// X = 0, R = masked F, (Jacobi) Z = dinv R, P = Z; partials: [0] = r.r (= b.b), [1] = r.z
+template <int KP>
+__global__ void __launch_bounds__(TB) k_init(const double* __restrict__ F, const uint8_t* __restrict__ constrained,
+                                             const double* __restrict__ dinv, double* __restrict__ X, double* __restrict__ R,
+                                             double* __restrict__ Z, double* __restrict__ P, int k, int64_t n, int jacobi,
+                                             double* __restrict__ partial) {
+  const int r = threadIdx.x % KP, g = threadIdx.x / KP;
+  constexpr int G = TB / KP;
+  double rr = 0.0, rz = 0.0;
+  if (r < k)
+    for (int64_t i = (int64_t)blockIdx.x * G + g; i < n; i += (int64_t)gridDim.x * G) {
+      const int64_t idx = i * k + r;
+      const double f = constrained[i] ? 0.0 : F[idx];
+      X[idx] = 0.0;
+      R[idx] = f;
+      rr = fma(f, f, rr);
+      if (jacobi) {
+        const double z = dinv[i] * f;
+        Z[idx] = z;
+        P[idx] = z;
+        rz = fma(f, z, rz);
+      }
+    }
+  block_partials<KP>(rr, rz, partial, 2);
+}
+
+// x += alpha p ; r -= alpha q ; (Jacobi) z = dinv r ; partials [0] = r.r, [1] = r.z
+template <int KP>
+__global__ void __launch_bounds__(TB) k_update_xr(double* __restrict__ X, double* __restrict__ R, const double* __restrict__ P,
+                                                  const double* __restrict__ Q, const double* __restrict__ dinv,
+                                                  double* __restrict__ Z, const double* __restrict__ scal, int k, int64_t n,
+                                                  int jacobi, double* __restrict__ partial) {
+  const int r = threadIdx.x % KP, g = threadIdx.x / KP;
+  constexpr int G = TB / KP;
+  double rr = 0.0, rz = 0.0;
+  if (r < k) {
+    const double alpha = scal[S_ALPHA * KMAX + r];
+    for (int64_t i = (int64_t)blockIdx.x * G + g; i < n; i += (int64_t)gridDim.x * G) {
+      const int64_t idx = i * k + r;
+      X[idx] = fma(alpha, P[idx], X[idx]);
+      const double res = fma(-alpha, Q[idx], R[idx]);
+      R[idx] = res;
+      rr = fma(res, res, rr);
+      if (jacobi) {
+        const double z = dinv[i] * res;
+        Z[idx] = z;
+        rz = fma(res, z, rz);
+      }
+    }
+  }
+  block_partials<KP>(rr, rz, partial, 2);
+}
+
+// partial [1] = r.z for a general preconditioner
+template <int KP>
+__global__ void __launch_bounds__(TB) k_dot_rz(const double* __restrict__ R, const double* __restrict__ Z, int k, int64_t n,
+                                               double* __restrict__ partial) {
+  const int r = threadIdx.x % KP, g = threadIdx.x / KP;
+  constexpr int G = TB / KP;
+  double rz = 0.0;
+  if (r < k)
+    for (int64_t i = (int64_t)blockIdx.x * G + g; i < n; i += (int64_t)gridDim.x * G) rz = fma(R[i * k + r], Z[i * k + r], rz);
+  __shared__ double sh[TB];
+  sh[threadIdx.x] = rz;
+  __syncthreads();
+  if (threadIdx.x < KP) {
+    double t = 0.0;
+    for (int i = threadIdx.x; i < TB; i += KP) t += sh[i];
+    partial[((int64_t)blockIdx.x * 2 + 1) * KMAX + threadIdx.x] = t;
+  }
+}
+
+// p = z + beta p
+template <int KP>
+__global__ void __launch_bounds__(TB) k_update_p(double* __restrict__ P, const double* __restrict__ Z,
+                                                 const double* __restrict__ scal, int k, int64_t n) {
+  const int r = threadIdx.x % KP, g = threadIdx.x / KP;
+  constexpr int G = TB / KP;
+  if (r >= k) return;
+  const double beta = scal[S_BETA * KMAX + r];
+  for (int64_t i = (int64_t)blockIdx.x * G + g; i < n; i += (int64_t)gridDim.x * G) {
+    const int64_t idx = i * k + r;
+    P[idx] = fma(beta, P[idx], Z[idx]);
+  }
+}
+
+// ---- one-block scalar kernels: finish the reductions in a fixed order (32 x 32 threads: column r, strip j)
+__device__ __forceinline__ double reduce_partials(const double* __restrict__ partial, int nblk, int stride, int slot) {
+  const int r = threadIdx.x & 31, j = threadIdx.x >> 5;  // blockDim = 1024
+  double t = 0.0;
+  for (int b = j; b < nblk; b += 32) t += partial[((int64_t)b * stride + slot) * KMAX + r];
+  __shared__ double sh[32][33];
+  __syncthreads();
+  sh[j][r] = t;
+  __syncthreads();
+  double tot = 0.0;
+  if (j == 0)
+    for (int q = 0; q < 32; q++) tot += sh[q][r];
+  return tot;  // valid for j == 0
+}
+
+// after k_init: bb = rr, rz, active, tolerance
+__global__ void k_scal_init(const double* __restrict__ partial, int nblk, double* __restrict__ scal, int* __restrict__ iters,
+                            int k, double rtol) {
+  const double rr = reduce_partials(partial, nblk, 2, 0);
+  const double rz = reduce_partials(partial, nblk, 2, 1);
+  if (threadIdx.x < KMAX) {
+    const int r = threadIdx.x;
+    const bool act = r < k && rr > 0.0;
+    scal[S_BB * KMAX + r] = rr;
+    scal[S_RR * KMAX + r] = rr;
+    scal[S_RZ * KMAX + r] = rz;
+    scal[S_TOL2 * KMAX + r] = rtol * rtol * rr;
+    scal[S_ACTIVE * KMAX + r] = act ? 1.0 : 0.0;
+    scal[S_ALPHA * KMAX + r] = 0.0;
+    scal[S_BETA * KMAX + r] = 0.0;
+    iters[r] = 0;
+  }
+}
+
+// rz only (general preconditioner path, after the first apply)
+__global__ void k_scal_rz0(const double* __restrict__ partial, int nblk, double* __restrict__ scal) {
+  const double rz = reduce_partials(partial, nblk, 2, 1);
+  if (threadIdx.x < KMAX) scal[S_RZ * KMAX + threadIdx.x] = rz;
+}
+
+// after the SpMM: alpha = rz / p.q
+__global__ void k_scal_alpha(const double* __restrict__ partial, int nblk, double* __restrict__ scal) {
+  const double pq = reduce_partials(partial, nblk, 1, 0);
+  if (threadIdx.x < KMAX) {
+    const int r = threadIdx.x;
+    const bool act = scal[S_ACTIVE * KMAX + r] != 0.0;
+    scal[S_PQ * KMAX + r] = pq;
+    scal[S_ALPHA * KMAX + r] = (act && pq > 0.0) ? scal[S_RZ * KMAX + r] / pq : 0.0;
+  }
+}
+
+// after the residual update (+ preconditioner): rr, convergence, beta = rz_new / rz
+__global__ void k_scal_beta(const double* __restrict__ partial, int nblk, double* __restrict__ scal, int* __restrict__ iters) {
+  const double rr = reduce_partials(partial, nblk, 2, 0);
+  const double rzn = reduce_partials(partial, nblk, 2, 1);
+  if (threadIdx.x < KMAX) {
+    const int r = threadIdx.x;
+    bool act = scal[S_ACTIVE * KMAX + r] != 0.0;
+    if (act) {
+      iters[r] += 1;
+      scal[S_RR * KMAX + r] = rr;
+      const double rz = scal[S_RZ * KMAX + r];
+      if (rr <= scal[S_TOL2 * KMAX + r] || !(rz > 0.0)) {
+        act = false;
+        scal[S_ACTIVE * KMAX + r] = 0.0;
+      }
+      scal[S_BETA * KMAX + r] = act ? rzn / rz : 0.0;
+      scal[S_RZ * KMAX + r] = rzn;
+    } else {
+      scal[S_BETA * KMAX + r] = 0.0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Jacobi: dinv = 1/diag on free dofs, 0 on constrained
+// ------------------------------------------------------------------------------------------------
+__global__ void k_dinv(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
+                       const uint8_t* __restrict__ constrained, double* __restrict__ dinv, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double d = 0.0;
+  if (!constrained[i]) {
+    int64_t lo = rowptr[i], hi = rowptr[i + 1];
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if (col[mid] < (int32_t)i) lo = mid + 1; else hi = mid;
+    }
+    if (lo < rowptr[i + 1] && col[lo] == (int32_t)i && val[lo] > 0.0) d = 1.0 / val[lo];
+  }
+  dinv[i] = d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// point sources, sampling, apparent resistivity
+// ------------------------------------------------------------------------------------------------
+__global__ void k_point_sources(SpaceView s, int nrhs, const int64_t* __restrict__ src_ptr, const double* __restrict__ src_z,
+                                const double* __restrict__ src_fac, double* __restrict__ F, int* __restrict__ bad) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrhs) return;
+  for (int64_t i = src_ptr[r]; i < src_ptr[r + 1]; i++) {
+    const double fac = src_fac[i];
+    if (fac == 0.0) continue;
+    int64_t dof[4];
+    double val[4];
+    const int m = axis_shape(s, src_z[i], dof, val);
+    if (m <= 0) { atomicExch(bad, m == 0 ? 1 : 2); continue; }
+    for (int q = 0; q < m; q++) F[dof[q] * nrhs + r] += fac * val[q];  // one thread per column: no race
+  }
+}
+
+__device__ __forceinline__ double eval_axis(const SpaceView& s, const double* __restrict__ X, int nrhs, int rhs, double z,
+                                            int* bad) {
+  int64_t dof[4];
+  double val[4];
+  const int m = axis_shape(s, z, dof, val);
+  if (m <= 0) { atomicExch(bad, m == 0 ? 1 : 2); return nan(""); }
+  double u = 0.0;
+  for (int q = 0; q < m; q++) u = fma(val[q], X[dof[q] * nrhs + rhs], u);
+  return u;
+}
+
+__global__ void k_sample(SpaceView s, const double* __restrict__ X, int nrhs, int npts, const int32_t* __restrict__ pt_rhs,
+                         const double* __restrict__ z, double* __restrict__ out, int* __restrict__ bad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npts) return;
+  const int rhs = pt_rhs ? pt_rhs[i] : 0;
+  if (rhs < 0 || rhs >= nrhs) { atomicExch(bad, 3); out[i] = nan(""); return; }
+  out[i] = eval_axis(s, X, nrhs, rhs, z[i], bad);
+}
+
+__global__ void k_resistivity(SpaceView s, const double* __restrict__ X, int nrhs, int npts, const int32_t* __restrict__ pt_rhs,
+                              const double* __restrict__ z0, const double* __restrict__ z1, const double* __restrict__ kf,
+                              double scale, double* __restrict__ ra, int* __restrict__ bad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npts) return;
+  const int rhs = pt_rhs[i];
+  if (rhs < 0 || rhs >= nrhs) { atomicExch(bad, 3); ra[i] = nan(""); return; }
+  const double u0 = eval_axis(s, X, nrhs, rhs, z0[i], bad);
+  double du = u0;
+  if (z1[i] == z1[i]) du = eval_axis(s, X, nrhs, rhs, z1[i], bad) - u0;
+  ra[i] = fabs(kf[i] * du) * scale;
+}
+
+int kp_for(int k) {
+  int kp = 1;
+  while (kp < k) kp <<= 1;
+  return kp;
+}
+
+#define DISPATCH_KP(kp, CALL)        \
+  switch (kp) {                      \
+    case 1: { constexpr int KP = 1; CALL; } break;   \
+    case 2: { constexpr int KP = 2; CALL; } break;   \
+    case 4: { constexpr int KP = 4; CALL; } break;   \
+    case 8: { constexpr int KP = 8; CALL; } break;   \
+    case 16: { constexpr int KP = 16; CALL; } break; \
+    default: { constexpr int KP = 32; CALL; } break; \
+  }
+
+int vec_grid(Ctx* c) { return c->num_sms * 8; }
+int spmm_grid(Ctx* c) { return c->num_sms * 8; }
+
+void check_bad(Ctx* c, DBuf<int>& bad, const char* who) {
+  int h = 0;
+  CK(cudaMemcpyAsync(&h, bad.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  bad.release(c->stream);
+  if (h == 1) FAIL(REMO_ERR_MESH, "%s: an axis point lies outside the mesh axis", who);
+  if (h == 2) FAIL(REMO_ERR_MESH, "%s: consecutive axis vertices are not joined by a mesh edge", who);
+  if (h == 3) FAIL(REMO_ERR_ARG, "%s: right-hand-side index out of range", who);
+}
+
+}  // namespace
+
+void alloc_solver_state(Ctx* c, int nrhs) {
+  cudaStream_t st = c->stream;
+  const size_t n = (size_t)c->ndof * nrhs;
+  c->F.ensure(n, st); c->X.ensure(n, st); c->R.ensure(n, st);
+  c->Z.ensure(n, st); c->P.ensure(n, st); c->Q.ensure(n, st);
+  c->partial.ensure((size_t)std::max(vec_grid(c), spmm_grid(c)) * 2 * KMAX, st);
+  c->scal.ensure(S_NSLOT * KMAX, st);
+  c->iters_d.ensure(KMAX, st);
+  c->nrhs = nrhs;
+}
+
+void launch_spmm(Ctx* c, const double* P, double* Q, int nrhs) {
+  const int kp = kp_for(nrhs);
+  const int grid = spmm_grid(c);
+  DISPATCH_KP(kp, (k_spmm<KP><<<grid, TB, 0, c->stream>>>(c->rowptr.p, c->col.p, c->val.p, c->constrained.p, P, Q, nrhs, c->ndof, c->partial.p)));
+  c->launches++;
+  CK(cudaGetLastError());
+}
+
+void launch_vector_updates(Ctx* c, int nrhs) {
+  const int kp = kp_for(nrhs);
+  const int grid = vec_grid(c);
+  DISPATCH_KP(kp, (k_update_xr<KP><<<grid, TB, 0, c->stream>>>(c->X.p, c->R.p, c->P.p, c->Q.p, c->dinv.p, c->Z.p, c->scal.p, nrhs, c->ndof, 1, c->partial.p)));
+  DISPATCH_KP(kp, (k_update_p<KP><<<grid, TB, 0, c->stream>>>(c->P.p, c->Z.p, c->scal.p, nrhs, c->ndof)));
+  c->launches += 2;
+  CK(cudaGetLastError());
+}
+
+void precond_setup(Ctx* c, int kind) {
+  if (!c->have_matrix) FAIL(REMO_ERR_STATE, "remo_precond_setup: no matrix (call remo_assemble first)");
+  if (kind != REMO_PRECOND_LOCAL && kind != REMO_PRECOND_MULTIGRID) FAIL(REMO_ERR_ARG, "remo_precond_setup: unknown preconditioner kind %d", kind);
+  StageTimer timer(c, ST_PRECOND);
+  c->dinv.ensure(c->ndof, c->stream);
+  LAUNCH(c, k_dinv, grid_for(c->ndof, TB), TB, 0, c->rowptr.p, c->col.p, c->val.p, c->constrained.p, c->dinv.p, c->ndof);
+  if (kind == REMO_PRECOND_MULTIGRID) FAIL(REMO_ERR_ARG, "remo_precond_setup: two-level preconditioner not built yet");
+  c->pkind = kind;
+}
+
+void rhs_point_sources(Ctx* c, int nrhs, const int64_t* src_ptr, const double* src_z, const double* src_fac) {
+  if (!c->have_space) FAIL(REMO_ERR_STATE, "remo_rhs_point_sources: no space (call remo_space_build first)");
+  if (nrhs < 1 || nrhs > REMO_MAX_RHS) FAIL(REMO_ERR_ARG, "remo_rhs_point_sources: nrhs must be in 1..%d (got %d)", REMO_MAX_RHS, nrhs);
+  StageTimer timer(c, ST_RHS);
+  cudaStream_t st = c->stream;
+  alloc_solver_state(c, nrhs);
+  std::vector<int64_t> hp(nrhs + 1);
+  CK(cudaMemcpyAsync(hp.data(), src_ptr, (nrhs + 1) * sizeof(int64_t), cudaMemcpyDefault, st));
+  CK(cudaStreamSynchronize(st));
+  const int64_t ns = hp[nrhs];
+  if (hp[0] != 0 || ns < 0) FAIL(REMO_ERR_ARG, "remo_rhs_point_sources: malformed src_ptr");
+  DBuf<int64_t> dp;
+  DBuf<double> dz, df;
+  DBuf<int> bad;
+  dp.ensure(nrhs + 1, st); dz.ensure(ns + 1, st); df.ensure(ns + 1, st); bad.ensure(1, st);
+  CK(cudaMemcpyAsync(dp.p, hp.data(), (nrhs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  if (ns) {
+    CK(cudaMemcpyAsync(dz.p, src_z, ns * sizeof(double), cudaMemcpyDefault, st));
+    CK(cudaMemcpyAsync(df.p, src_fac, ns * sizeof(double), cudaMemcpyDefault, st));
+  }
+  CK(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+  CK(cudaMemsetAsync(c->F.p, 0, (size_t)c->ndof * nrhs * sizeof(double), st));
+  LAUNCH(c, k_point_sources, 1, 32, 0, make_view(c), nrhs, dp.p, dz.p, df.p, c->F.p, bad.p);
+  check_bad(c, bad, "remo_rhs_point_sources");
+  dp.release(st); dz.release(st); df.release(st);
+  c->have_rhs = true;
+  c->have_solution = false;
+}
+
+int solve(Ctx* c, double rtol, int maxit, int* iters, double* relres) {
+  if (!c->have_matrix || c->pkind < 0) FAIL(REMO_ERR_STATE, "remo_solve: matrix / preconditioner missing (remo_assemble, remo_precond_setup)");
+  if (!c->have_rhs) FAIL(REMO_ERR_STATE, "remo_solve: no right-hand side (call remo_rhs_point_sources first)");
+  if (!(rtol > 0.0) || maxit < 1) FAIL(REMO_ERR_ARG, "remo_solve: rtol must be > 0 and maxit >= 1");
+  StageTimer timer(c, ST_SOLVE);
+  cudaStream_t st = c->stream;
+  const int k = c->nrhs, kp = kp_for(k);
+  const int64_t n = c->ndof;
+  const int vg = vec_grid(c), sg = spmm_grid(c);
+  const int jac = 1;
+
+  DISPATCH_KP(kp, (k_init<KP><<<vg, TB, 0, st>>>(c->F.p, c->constrained.p, c->dinv.p, c->X.p, c->R.p, c->Z.p, c->P.p, k, n, jac, c->partial.p)));
+  k_scal_init<<<1, 1024, 0, st>>>(c->partial.p, vg, c->scal.p, c->iters_d.p, k, rtol);
+  c->launches += 2;
+  CK(cudaGetLastError());
+
+  const int check_every = 16;
+  std::vector<double> hs(S_NSLOT * KMAX);
+  int it = 0;
+  bool done = false;
+  while (it < maxit && !done) {
+    const int chunk = std::min(check_every, maxit - it);
+    for (int q = 0; q < chunk; q++) {
+      const size_t pe = (size_t)2 * (it + q);
+      if (c->prof) {
+        while (c->prof_ev.size() < pe + 2) {
+          cudaEvent_t e;
+          CK(cudaEventCreate(&e));
+          c->prof_ev.push_back(e);
+        }
+        CK(cudaEventRecord(c->prof_ev[pe], st));
+      }
+      launch_spmm(c, c->P.p, c->Q.p, k);
+      if (c->prof) CK(cudaEventRecord(c->prof_ev[pe + 1], st));
+      k_scal_alpha<<<1, 1024, 0, st>>>(c->partial.p, sg, c->scal.p);
+      DISPATCH_KP(kp, (k_update_xr<KP><<<vg, TB, 0, st>>>(c->X.p, c->R.p, c->P.p, c->Q.p, c->dinv.p, c->Z.p, c->scal.p, k, n, jac, c->partial.p)));
+      k_scal_beta<<<1, 1024, 0, st>>>(c->partial.p, vg, c->scal.p, c->iters_d.p);
+      DISPATCH_KP(kp, (k_update_p<KP><<<vg, TB, 0, st>>>(c->P.p, c->Z.p, c->scal.p, k, n)));
+      c->launches += 4;
+    }
+    CK(cudaGetLastError());
+    it += chunk;
+    CK(cudaMemcpyAsync(hs.data(), c->scal.p, hs.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    done = true;
+    for (int r = 0; r < k; r++)
+      if (hs[S_ACTIVE * KMAX + r] != 0.0) done = false;
+  }
+  std::vector<int> hit(KMAX);
+  CK(cudaMemcpyAsync(hit.data(), c->iters_d.p, KMAX * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  bool conv = true;
+  for (int r = 0; r < k; r++) {
+    const double bb = hs[S_BB * KMAX + r], rr = hs[S_RR * KMAX + r];
+    const double rel = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+    if (iters) iters[r] = hit[r];
+    if (relres) relres[r] = rel;
+    if (hs[S_ACTIVE * KMAX + r] != 0.0) conv = false;
+  }
+  if (c->prof) {
+    for (int q = 0; q < it; q++) {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, c->prof_ev[2 * q], c->prof_ev[2 * q + 1]));
+      c->prof_spmm_ms += ms;
+    }
+    c->prof_spmm_n += it;
+  }
+  c->have_solution = true;
+  c->host_scal = hs;
+  return conv ? REMO_OK : REMO_ERR_NOCONV;
+}
+
+void sample_axis(Ctx* c, int npts, const int32_t* pt_rhs, const double* z, double* out) {
+  if (!c->have_solution) FAIL(REMO_ERR_STATE, "remo_sample_axis: no solution (call remo_solve first)");
+  if (npts < 1) return;
+  StageTimer timer(c, ST_SAMPLE);
+  cudaStream_t st = c->stream;
+  DBuf<int32_t> dr;
+  DBuf<double> dz, dout;
+  DBuf<int> bad;
+  dr.ensure(npts, st); dz.ensure(npts, st); dout.ensure(npts, st); bad.ensure(1, st);
+  if (pt_rhs) CK(cudaMemcpyAsync(dr.p, pt_rhs, npts * sizeof(int32_t), cudaMemcpyDefault, st));
+  CK(cudaMemcpyAsync(dz.p, z, npts * sizeof(double), cudaMemcpyDefault, st));
+  CK(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+  LAUNCH(c, k_sample, grid_for(npts, 128), 128, 0, make_view(c), c->X.p, c->nrhs, npts, pt_rhs ? dr.p : nullptr, dz.p, dout.p, bad.p);
+  CK(cudaMemcpyAsync(out, dout.p, npts * sizeof(double), cudaMemcpyDefault, st));
+  check_bad(c, bad, "remo_sample_axis");
+  dr.release(st); dz.release(st); dout.release(st);
+}
+
+void apparent_resistivity(Ctx* c, int npts, const int32_t* pt_rhs, const double* z0, const double* z1, const double* kf,
+                          double scale, double* ra) {
+  if (!c->have_solution) FAIL(REMO_ERR_STATE, "remo_apparent_resistivity: no solution (call remo_solve first)");
+  if (npts < 1) return;
+  StageTimer timer(c, ST_SAMPLE);
+  cudaStream_t st = c->stream;
+  DBuf<int32_t> dr;
+  DBuf<double> d0, d1, dk, dout;
+  DBuf<int> bad;
+  dr.ensure(npts, st); d0.ensure(npts, st); d1.ensure(npts, st); dk.ensure(npts, st); dout.ensure(npts, st); bad.ensure(1, st);
+  CK(cudaMemcpyAsync(dr.p, pt_rhs, npts * sizeof(int32_t), cudaMemcpyDefault, st));
+  CK(cudaMemcpyAsync(d0.p, z0, npts * sizeof(double), cudaMemcpyDefault, st));
+  CK(cudaMemcpyAsync(d1.p, z1, npts * sizeof(double), cudaMemcpyDefault, st));
+  CK(cudaMemcpyAsync(dk.p, kf, npts * sizeof(double), cudaMemcpyDefault, st));
+  CK(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+  LAUNCH(c, k_resistivity, grid_for(npts, 128), 128, 0, make_view(c), c->X.p, c->nrhs, npts, dr.p, d0.p, d1.p, dk.p, scale, dout.p, bad.p);
+  CK(cudaMemcpyAsync(ra, dout.p, npts * sizeof(double), cudaMemcpyDefault, st));
+  check_bad(c, bad, "remo_apparent_resistivity");
+  dr.release(st); d0.release(st); d1.release(st); dk.release(st); dout.release(st);
+}

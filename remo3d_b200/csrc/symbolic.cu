@@ -1,0 +1,378 @@
+// Symbolic phase on the GPU: topology (edges, faces), dof numbering, Dirichlet dofs, dof -> element
+// adjacency and the CSR sparsity pattern.  Replaces the space construction
+// `fes = ngs.H1(mesh, order=3, dirichlet=...)` (/root/reference/remo3d/ngsolve_functions.py:27) and the
+// sparsity-graph part of `a.Assemble()` (:47).  Numbering contract: SURVEY.md section 10.2 /
+// oracle/fem_oracle.py `Space` (edges and faces numbered lexicographically by sorted vertex tuples).
+//
+// Everything is integer work; sorting / scanning uses CUB device primitives, the rest are small
+// hand-written kernels.  The only host synchronisations are the reads of ne, nf and nnz (needed to
+// size the allocations).
+#include <cub/cub.cuh>
+
+#include "space_view.cuh"
+
+namespace {
+
+constexpr int TB = 256;
+
+__device__ __forceinline__ void cswap(int32_t& a, int32_t& b) {
+  if (a > b) { int32_t t = a; a = b; b = t; }
+}
+
+__global__ void k_sort_verts(const int32_t* __restrict__ elems, int32_t* __restrict__ sv, int64_t nt, int nvl) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= nt) return;
+  if (nvl == 4) {
+    int4 e = reinterpret_cast<const int4*>(elems)[t];
+    int32_t a = e.x, b = e.y, c = e.z, d = e.w;
+    cswap(a, b); cswap(c, d); cswap(a, c); cswap(b, d); cswap(b, c);
+    reinterpret_cast<int4*>(sv)[t] = make_int4(a, b, c, d);
+  } else {
+    int32_t a = elems[3 * t], b = elems[3 * t + 1], c = elems[3 * t + 2];
+    cswap(a, b); cswap(b, c); cswap(a, b);
+    sv[3 * t] = a; sv[3 * t + 1] = b; sv[3 * t + 2] = c;
+  }
+}
+
+// one key per (element, local edge): (a<<32)|b, payload = flat index into elem_edges
+__global__ void k_edge_keys(const int32_t* __restrict__ sv, uint64_t* __restrict__ keys, uint32_t* __restrict__ pay,
+                            int64_t nt, int nvl, int nle) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nt * nle) return;
+  int64_t t = i / nle;
+  int le = (int)(i - t * nle);
+  int a = (nvl == 4) ? LE3[le][0] : LE2[le][0];
+  int b = (nvl == 4) ? LE3[le][1] : LE2[le][1];
+  keys[i] = ((uint64_t)(uint32_t)sv[t * nvl + a] << 32) | (uint32_t)sv[t * nvl + b];
+  pay[i] = (uint32_t)i;
+}
+
+// faces of tets: key = (edge(i,j) << 32) | k ; lexicographic in (i,j,k) because edge numbers are lexicographic in (i,j)
+__global__ void k_face_keys(const int32_t* __restrict__ sv, const int32_t* __restrict__ elem_edges,
+                            uint64_t* __restrict__ keys, uint32_t* __restrict__ pay, int64_t nt) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nt * 4) return;
+  int64_t t = i >> 2;
+  int lf = (int)(i & 3);
+  uint32_t e = (uint32_t)elem_edges[t * 6 + LF3_EDGE[lf]];
+  keys[i] = ((uint64_t)e << 32) | (uint32_t)sv[t * 4 + LF3_V[lf][2]];
+  pay[i] = (uint32_t)i;
+}
+
+__global__ void k_flag_first(const uint64_t* __restrict__ keys, int32_t* __restrict__ flag, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  flag[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+
+// id = inclusive_scan(flag) - 1 ; scatter ids back to the (element, local) slots and keep the unique keys
+__global__ void k_assign_ids(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ pay,
+                             const int32_t* __restrict__ scan, int32_t* __restrict__ elem_ids,
+                             uint64_t* __restrict__ uniq, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t id = scan[i] - 1;
+  elem_ids[pay[i]] = id;
+  if (i == 0 || keys[i] != keys[i - 1]) uniq[id] = keys[i];
+}
+
+__global__ void k_mark_dirichlet(SpaceView s, const int32_t* __restrict__ bfacets, const uint8_t* __restrict__ bdir,
+                                 int64_t nb, uint8_t* __restrict__ constrained, int* __restrict__ bad) {
+  int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (f >= nb || !bdir[f]) return;
+  const int d = s.dim;
+  int32_t v[3];
+  for (int i = 0; i < d; i++) v[i] = bfacets[f * d + i];
+  if (d == 3) { cswap(v[0], v[1]); cswap(v[1], v[2]); cswap(v[0], v[1]); } else { cswap(v[0], v[1]); }
+  for (int i = 0; i < d; i++) constrained[v[i]] = 1;
+  if (s.order == 1) return;
+  const int pe = s.order - 1;
+  int64_t e01 = -1;
+  for (int i = 0; i < d; i++)
+    for (int j = i + 1; j < d; j++) {
+      int64_t e = find_edge(s, v[i], v[j]);
+      if (e < 0) { atomicExch(bad, 1); continue; }
+      if (i == 0 && j == 1) e01 = e;
+      for (int k = 0; k < pe; k++) constrained[s.edge_base + pe * e + k] = 1;
+    }
+  if (s.order == 3 && d == 3 && e01 >= 0) {
+    uint64_t key = ((uint64_t)e01 << 32) | (uint32_t)v[2];
+    int64_t pos = lower_bound_u64(s.face_keys, s.nf, key);
+    if (pos < s.nf && s.face_keys[pos] == key) constrained[s.face_base + pos] = 1; else atomicExch(bad, 1);
+  }
+}
+
+// adjacency entries: key = global dof, payload = element*nld + local dof
+__global__ void k_adj_pairs(SpaceView s, uint32_t* __restrict__ keys, uint32_t* __restrict__ pay, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t t = i / s.nld;
+  int b = (int)(i - t * s.nld);
+  keys[i] = (uint32_t)elem_dof(s, t, b);
+  pay[i] = (uint32_t)i;
+}
+
+// adj_ptr[d] = first position whose key >= d (keys sorted); handles dofs without elements
+__global__ void k_adj_ptr(const uint32_t* __restrict__ keys, int64_t n, int64_t ndof, int64_t* __restrict__ ptr) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i > n) return;
+  int64_t prev = (i == 0) ? -1 : (int64_t)keys[i - 1];
+  int64_t cur = (i == n) ? ndof : (int64_t)keys[i];
+  for (int64_t d = prev + 1; d <= cur; d++) ptr[d] = i;
+}
+
+// candidate columns of every row: the nld dofs of each adjacent element
+__global__ void k_candidates(SpaceView s, const uint32_t* __restrict__ adj, int32_t* __restrict__ cand, int64_t nadj) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nadj * s.nld) return;
+  int64_t a = i / s.nld;
+  int b = (int)(i - a * s.nld);
+  int64_t t = adj[a] / s.nld;
+  cand[i] = (int32_t)elem_dof(s, t, b);
+}
+
+__global__ void k_flag_cols(const int32_t* __restrict__ cand, const uint32_t* __restrict__ adjkey, int nld,
+                            int32_t* __restrict__ flag, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t a = i / nld;
+  bool seg_start = (i - a * nld == 0) && (a == 0 || adjkey[a] != adjkey[a - 1]);
+  flag[i] = (seg_start || cand[i] != cand[i - 1]) ? 1 : 0;
+}
+
+__global__ void k_fill_csr(const int32_t* __restrict__ cand, const uint32_t* __restrict__ adjkey, int nld,
+                           const int32_t* __restrict__ scan, int64_t n, int64_t* __restrict__ rowptr,
+                           int32_t* __restrict__ col) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t a = i / nld;
+  bool seg_start = (i - a * nld == 0) && (a == 0 || adjkey[a] != adjkey[a - 1]);
+  bool first = seg_start || cand[i] != cand[i - 1];
+  if (first) col[scan[i] - 1] = cand[i];
+  if (seg_start) {
+    // rows without elements between the previous row and this one get empty ranges
+    int64_t row = adjkey[a];
+    int64_t prev = (a == 0) ? -1 : (int64_t)adjkey[a - 1];
+    for (int64_t d = prev + 1; d <= row; d++) rowptr[d] = scan[i] - 1;
+  }
+}
+
+__global__ void k_fill_tail(int64_t* __restrict__ rowptr, int64_t from, int64_t ndof, int64_t nnz) {
+  int64_t d = from + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (d <= ndof) rowptr[d] = nnz;
+}
+
+__global__ void k_unpack_edges(const uint64_t* __restrict__ keys, int64_t ne, int32_t* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= ne) return;
+  out[2 * i] = (int32_t)(keys[i] >> 32);
+  out[2 * i + 1] = (int32_t)(keys[i] & 0xffffffffu);
+}
+
+__global__ void k_unpack_faces(const uint64_t* __restrict__ fkeys, const uint64_t* __restrict__ ekeys, int64_t nf,
+                               int32_t* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nf) return;
+  uint64_t ek = ekeys[fkeys[i] >> 32];
+  out[3 * i] = (int32_t)(ek >> 32);
+  out[3 * i + 1] = (int32_t)(ek & 0xffffffffu);
+  out[3 * i + 2] = (int32_t)(fkeys[i] & 0xffffffffu);
+}
+
+int bits_for(uint64_t n) {
+  int b = 1;
+  while (b < 64 && (n >> b)) b++;
+  return b;
+}
+
+// sort (key,payload) pairs, number the distinct keys 0.. in ascending order; returns the count
+template <typename KeyT>
+int64_t sort_and_number(Ctx* c, DBuf<KeyT>& keys, DBuf<uint32_t>& pay, int64_t n, int end_bit, DBuf<KeyT>& keys_sorted,
+                        DBuf<uint32_t>& pay_sorted) {
+  keys_sorted.ensure(n, c->stream);
+  pay_sorted.ensure(n, c->stream);
+  size_t bytes = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys.p, keys_sorted.p, pay.p, pay_sorted.p, n, 0, end_bit, c->stream));
+  c->tmp.ensure(bytes, c->stream);
+  CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, keys.p, keys_sorted.p, pay.p, pay_sorted.p, n, 0, end_bit, c->stream));
+  c->launches += 4;
+  return n;
+}
+
+int32_t scan_flags(Ctx* c, DBuf<int32_t>& flag, DBuf<int32_t>& scan, int64_t n) {
+  scan.ensure(n, c->stream);
+  size_t bytes = 0;
+  CK(cub::DeviceScan::InclusiveSum(nullptr, bytes, flag.p, scan.p, n, c->stream));
+  c->tmp.ensure(bytes, c->stream);
+  CK(cub::DeviceScan::InclusiveSum(c->tmp.p, bytes, flag.p, scan.p, n, c->stream));
+  c->launches += 2;
+  int32_t total = 0;
+  CK(cudaMemcpyAsync(&total, scan.p + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return total;
+}
+
+struct ScaleOffsets {
+  const int64_t* ptr;
+  int nld;
+  __host__ __device__ int64_t operator()(int64_t i) const { return ptr[i] * nld; }
+};
+
+}  // namespace
+
+void space_build(Ctx* c, int order) {
+  if (!c->have_mesh) FAIL(REMO_ERR_STATE, "remo_space_build: no mesh (call remo_mesh_set first)");
+  if (order < 1 || order > 3) FAIL(REMO_ERR_ARG, "remo_space_build: order must be 1, 2 or 3 (got %d)", order);
+  StageTimer timer(c, ST_SPACE);
+  cudaStream_t st = c->stream;
+  const int dim = c->dim, nvl = dim + 1;
+  const int64_t nt = c->nt;
+  c->order = order;
+  c->nle = (dim == 3) ? 6 : 3;
+  c->nlf = (dim == 3) ? 4 : 1;
+  c->npair = nvl * (nvl + 1) / 2;
+  c->nld = nvl + c->nle * (order - 1) + (order == 3 ? c->nlf : 0);
+  c->have_space = c->have_matrix = false;
+  c->pkind = -1;
+
+  // 1. sorted element vertices
+  c->sv.ensure(nt * nvl, st);
+  LAUNCH(c, k_sort_verts, grid_for(nt, TB), TB, 0, c->elems.p, c->sv.p, nt, nvl);
+
+  DBuf<uint64_t> k64, k64s;
+  DBuf<uint32_t> pay, pays;
+  DBuf<int32_t> flag, scan;
+
+  // 2. edges (always built: order >= 2 needs the dofs, order 1 needs nothing but the cost is small and
+  //    remo_topology_get exports them)
+  {
+    const int64_t n = nt * c->nle;
+    k64.ensure(n, st); pay.ensure(n, st);
+    LAUNCH(c, k_edge_keys, grid_for(n, TB), TB, 0, c->sv.p, k64.p, pay.p, nt, nvl, c->nle);
+    sort_and_number(c, k64, pay, n, 32 + bits_for((uint64_t)c->nv), k64s, pays);
+    flag.ensure(n, st);
+    LAUNCH(c, k_flag_first, grid_for(n, TB), TB, 0, k64s.p, flag.p, n);
+    c->ne = scan_flags(c, flag, scan, n);
+    c->edge_keys.ensure(c->ne, st);
+    c->elem_edges.ensure(n, st);
+    LAUNCH(c, k_assign_ids, grid_for(n, TB), TB, 0, k64s.p, pays.p, scan.p, c->elem_edges.p, c->edge_keys.p, n);
+  }
+  // 3. faces (3D order 3 only); in 2D the order-3 cell bubbles are numbered by element
+  c->nf = 0;
+  if (order == 3 && dim == 3) {
+    const int64_t n = nt * 4;
+    k64.ensure(n, st); pay.ensure(n, st);
+    LAUNCH(c, k_face_keys, grid_for(n, TB), TB, 0, c->sv.p, c->elem_edges.p, k64.p, pay.p, nt);
+    sort_and_number(c, k64, pay, n, 32 + bits_for((uint64_t)c->ne), k64s, pays);
+    flag.ensure(n, st);
+    LAUNCH(c, k_flag_first, grid_for(n, TB), TB, 0, k64s.p, flag.p, n);
+    c->nf = scan_flags(c, flag, scan, n);
+    c->face_keys.ensure(c->nf, st);
+    c->elem_faces.ensure(n, st);
+    LAUNCH(c, k_assign_ids, grid_for(n, TB), TB, 0, k64s.p, pays.p, scan.p, c->elem_faces.p, c->face_keys.p, n);
+  } else if (order == 3 && dim == 2) {
+    c->nf = nt;
+  }
+  c->edge_base = c->nv;
+  c->face_base = c->nv + (int64_t)(order - 1) * c->ne;
+  c->ndof = c->face_base + (order == 3 ? c->nf : 0);
+  if (c->ndof >= (int64_t)1 << 31) FAIL(REMO_ERR_ARG, "remo_space_build: %lld dofs exceed the int32 column index", (long long)c->ndof);
+  k64.release(st); k64s.release(st);
+
+  SpaceView sview = make_view(c);
+
+  // 4. Dirichlet dofs
+  c->constrained.ensure(c->ndof, st);
+  CK(cudaMemsetAsync(c->constrained.p, 0, c->ndof, st));
+  if (c->nb > 0) {
+    DBuf<int> bad;
+    bad.ensure(1, st);
+    CK(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+    LAUNCH(c, k_mark_dirichlet, grid_for(c->nb, TB), TB, 0, sview, c->bfacets.p, c->bdir.p, c->nb, c->constrained.p, bad.p);
+    int hbad = 0;
+    CK(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    bad.release(st);
+    if (hbad) FAIL(REMO_ERR_MESH, "remo_space_build: a Dirichlet boundary facet is not a face of the mesh");
+  }
+
+  // 5. dof -> (element, local dof) adjacency, elements ascending within a dof (stable radix sort)
+  const int64_t nadj = nt * c->nld;
+  if (nadj >= (int64_t)1 << 32) FAIL(REMO_ERR_ARG, "remo_space_build: mesh too large (nt*nld >= 2^32)");
+  c->nadj = nadj;
+  DBuf<uint32_t> akey, akeys;
+  akey.ensure(nadj, st); pay.ensure(nadj, st);
+  LAUNCH(c, k_adj_pairs, grid_for(nadj, TB), TB, 0, sview, akey.p, pay.p, nadj);
+  c->adj.ensure(nadj, st);
+  {
+    akeys.ensure(nadj, st);
+    size_t bytes = 0;
+    const int eb = bits_for((uint64_t)c->ndof);
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, akey.p, akeys.p, pay.p, c->adj.p, nadj, 0, eb, st));
+    c->tmp.ensure(bytes, st);
+    CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, akey.p, akeys.p, pay.p, c->adj.p, nadj, 0, eb, st));
+    c->launches += 4;
+  }
+  akey.release(st); pay.release(st); pays.release(st);
+  c->adj_ptr.ensure(c->ndof + 1, st);
+  LAUNCH(c, k_adj_ptr, grid_for(nadj + 1, TB), TB, 0, akeys.p, nadj, c->ndof, c->adj_ptr.p);
+
+  // 6. CSR pattern: per row sort + unique of the candidate columns
+  const int64_t ncand = nadj * c->nld;
+  if (ncand >= (int64_t)1 << 31) FAIL(REMO_ERR_ARG, "remo_space_build: %lld candidate entries exceed the 2^31 limit of the pattern builder", (long long)ncand);
+  DBuf<int32_t> cand, cands;
+  cand.ensure(ncand, st); cands.ensure(ncand, st);
+  LAUNCH(c, k_candidates, grid_for(ncand, TB), TB, 0, sview, c->adj.p, cand.p, nadj);
+  {
+    cub::CountingInputIterator<int64_t> cnt(0);
+    cub::TransformInputIterator<int64_t, ScaleOffsets, cub::CountingInputIterator<int64_t>> begins(cnt, ScaleOffsets{c->adj_ptr.p, c->nld});
+    size_t bytes = 0;
+    CK(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, cand.p, cands.p, (int)ncand, (int)c->ndof, begins, begins + 1, st));
+    c->tmp.ensure(bytes, st);
+    CK(cub::DeviceSegmentedSort::SortKeys(c->tmp.p, bytes, cand.p, cands.p, (int)ncand, (int)c->ndof, begins, begins + 1, st));
+    c->launches += 4;
+  }
+  cand.release(st);
+  flag.ensure(ncand, st);
+  LAUNCH(c, k_flag_cols, grid_for(ncand, TB), TB, 0, cands.p, akeys.p, c->nld, flag.p, ncand);
+  c->nnz = scan_flags(c, flag, scan, ncand);
+  c->rowptr.ensure(c->ndof + 1, st);
+  c->col.ensure(c->nnz, st);
+  c->val.ensure(c->nnz, st);
+  LAUNCH(c, k_fill_csr, grid_for(ncand, TB), TB, 0, cands.p, akeys.p, c->nld, scan.p, ncand, c->rowptr.p, c->col.p);
+  {
+    // rows after the last one that has elements (and the terminating entry)
+    uint32_t last = 0;
+    CK(cudaMemcpyAsync(&last, akeys.p + (nadj - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int64_t from = (int64_t)last + 1;
+    LAUNCH(c, k_fill_tail, grid_for(c->ndof + 1 - from, TB), TB, 0, c->rowptr.p, from, c->ndof, c->nnz);
+  }
+  cands.release(st); flag.release(st); scan.release(st); akeys.release(st);
+  c->have_space = true;
+}
+
+void topology_get(Ctx* c, int32_t* edges, int32_t* faces, int32_t* elem_edges, int32_t* elem_faces) {
+  if (!c->have_space) FAIL(REMO_ERR_STATE, "remo_topology_get: no space (call remo_space_build first)");
+  cudaStream_t st = c->stream;
+  if (edges && c->ne) {
+    DBuf<int32_t> t;
+    t.ensure(2 * c->ne, st);
+    LAUNCH(c, k_unpack_edges, grid_for(c->ne, TB), TB, 0, c->edge_keys.p, c->ne, t.p);
+    CK(cudaMemcpyAsync(edges, t.p, 2 * c->ne * sizeof(int32_t), cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
+    t.release(st);
+  }
+  if (faces && c->nf && c->dim == 3) {
+    DBuf<int32_t> t;
+    t.ensure(3 * c->nf, st);
+    LAUNCH(c, k_unpack_faces, grid_for(c->nf, TB), TB, 0, c->face_keys.p, c->edge_keys.p, c->nf, t.p);
+    CK(cudaMemcpyAsync(faces, t.p, 3 * c->nf * sizeof(int32_t), cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
+    t.release(st);
+  }
+  if (elem_edges) CK(cudaMemcpyAsync(elem_edges, c->elem_edges.p, c->nt * c->nle * sizeof(int32_t), cudaMemcpyDefault, st));
+  if (elem_faces && c->order == 3 && c->dim == 3)
+    CK(cudaMemcpyAsync(elem_faces, c->elem_faces.p, c->nt * 4 * sizeof(int32_t), cudaMemcpyDefault, st));
+  CK(cudaStreamSynchronize(st));
+}

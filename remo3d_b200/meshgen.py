@@ -1,0 +1,363 @@
+"""Synthetic tetrahedral meshers (host side).
+
+The reference meshes with Gmsh (3D half-ball, `gmsh_functions.py:544-684`) or Netgen (2D); mesh
+generation stays on the host cores in this design (BASELINE.json north_star) and neither mesher is
+installable in this image, so tests and benchmarks use the generators below.  They reproduce the
+*properties the solve depends on* of the reference's 3D meshes:
+
+  * half-ball y >= 0 of radius `domain_radius` around the batch centre, symmetry plane y = 0 with a
+    natural boundary condition, outer sphere = 'dirichlet_boundary' made of the boundary faces whose
+    three nodes lie on |x| = R (`gmsh_functions.py:581, 648-658`);
+  * the electrode axis x = y = 0 is a chain of mesh edges and every electrode is a vertex
+    (`gmsh_functions.py:552-575`);
+  * element size graded from `h_electrode` at the electrodes to `h_max` at the boundary
+    (`gmsh_functions.py:630-645`);
+  * material index per tet, 0 = borehole mud, then per layer top->bottom flushed zone (if any) and
+    undisturbed zone (`gmsh_functions.py:592-624`), here assigned from the tet centroid.
+
+Point cloud = nested, slightly jittered body-centred-cubic lattices (level l has spacing
+h_max / 2^l and is used where the size field asks for it) + exact axis / symmetry-plane / sphere
+points; tets = scipy.spatial.Delaunay (Qhull); boundary slivers are peeled.
+"""
+from itertools import permutations
+
+import numpy as np
+
+# ----------------------------------------------------------------------------------------------
+# structured box (unit tests, patch tests)
+# ----------------------------------------------------------------------------------------------
+_KUHN = []
+for _perm in permutations(range(3)):
+    _v = [0, 0, 0]
+    _path = [0]
+    for _ax in _perm:
+        _v[_ax] = 1
+        _path.append(_v[0] + 2 * _v[1] + 4 * _v[2])
+    _KUHN.append(_path)
+
+
+def box_mesh(n, lo=(0.0, 0.0, -1.0), hi=(1.0, 1.0, 1.0), dirichlet=lambda c: np.ones(c.shape[0], bool)):
+    """Kuhn-split structured tet mesh of a box; the edge x=lo[0], y=lo[1] is a chain of mesh edges.
+
+    `n` = cells per direction (int or 3-tuple).  Returns arrays (points, elems, bfacets, bc) with
+    bc 1 = natural, 2 = 'dirichlet_boundary' where `dirichlet(facet centroids)` is true."""
+    nx, ny, nz = (n, n, n) if np.isscalar(n) else n
+    xs = [np.linspace(lo[d], hi[d], m + 1) for d, m in enumerate((nx, ny, nz))]
+    X, Y, Z = np.meshgrid(*xs, indexing="ij")
+    pts = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+
+    def vid(i, j, k):
+        return (i * (ny + 1) + j) * (nz + 1) + k
+
+    I, J, K = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    I, J, K = I.ravel(), J.ravel(), K.ravel()
+    corner = np.stack([vid(I + (c & 1), J + ((c >> 1) & 1), K + ((c >> 2) & 1)) for c in range(8)], axis=1)
+    elems = np.concatenate([corner[:, path] for path in _KUHN], axis=0).astype(np.int32)
+    bfacets = boundary_facets(elems)
+    cen = pts[bfacets].mean(axis=1)
+    bc = np.where(dirichlet(cen), 2, 1).astype(np.int32)
+    return pts, elems, bfacets, bc
+
+
+def _facet_keys(facets, nv):
+    """Order-independent int64 key of each facet (vertex numbers < 2^21 for triangles)."""
+    f = np.sort(facets.astype(np.int64), axis=1)
+    key = f[:, 0]
+    for c in range(1, f.shape[1]):
+        key = key * nv + f[:, c]
+    return key
+
+
+def boundary_facets(elems, return_owner=False):
+    """Faces that belong to exactly one tet (triangles) / edges of exactly one triangle."""
+    d1 = elems.shape[1]
+    nv = int(elems.max()) + 1
+    if d1 == 4 and nv >= (1 << 21):
+        raise ValueError("boundary_facets: more than 2^21 vertices not supported by the host mesher")
+    faces = np.concatenate([np.delete(elems, i, axis=1) for i in range(d1)], axis=0)
+    _, idx, cnt = np.unique(_facet_keys(faces, nv), return_index=True, return_counts=True)
+    sel = idx[cnt == 1]
+    if return_owner:
+        return faces[sel].astype(np.int32), sel % elems.shape[0]
+    return faces[sel].astype(np.int32)
+
+
+# ----------------------------------------------------------------------------------------------
+# graded half-ball
+# ----------------------------------------------------------------------------------------------
+class SizeField:
+    """h(x) = min( h_electrode + g*dist(electrodes),  h_axis + g*dist(tool segment),  h_max )."""
+
+    def __init__(self, electrodes_z, h_electrode, h_axis, h_max, grading):
+        self.ez = np.asarray(sorted(electrodes_z), dtype=float)
+        self.h_e, self.h_a, self.h_max, self.g = h_electrode, h_axis, h_max, grading
+        self.z_lo, self.z_hi = self.ez[0], self.ez[-1]
+
+    def __call__(self, p):
+        p = np.atleast_2d(p)
+        rho2 = p[:, 0] ** 2 + p[:, 1] ** 2
+        z = p[:, 2]
+        j = np.clip(np.searchsorted(self.ez, z), 1, self.ez.shape[0] - 1) if self.ez.shape[0] > 1 else np.zeros(z.shape, int)
+        if self.ez.shape[0] > 1:
+            dz = np.minimum(np.abs(z - self.ez[j - 1]), np.abs(z - self.ez[j]))
+        else:
+            dz = np.abs(z - self.ez[0])
+        d_e = np.sqrt(rho2 + dz ** 2)
+        zc = np.clip(z, self.z_lo, self.z_hi)
+        d_a = np.sqrt(rho2 + (z - zc) ** 2)
+        return np.minimum(np.minimum(self.h_e + self.g * d_e, self.h_a + self.g * d_a), self.h_max)
+
+
+def _axis_points(size, radius):
+    """Graded 1-D subdivision of [-R, R] containing every electrode exactly."""
+    must = np.unique(np.concatenate([[-radius, radius], size.ez]))
+    zs = list(must)
+    stack = list(zip(must[:-1], must[1:]))
+    while stack:
+        a, b = stack.pop()
+        mid = 0.5 * (a + b)
+        if (b - a) > size(np.array([[0.0, 0.0, mid]]))[0]:
+            zs.append(mid)
+            stack.append((a, mid))
+            stack.append((mid, b))
+    return np.unique(np.asarray(zs))
+
+
+def _bcc_level_points(level, s, size, radius, rng, jitter, half):
+    """New BCC lattice points of this level (spacing s) wherever the size field is finer than 2s."""
+    u = s / 2.0  # integer unit
+    # region where h < 2s  ->  inside a capsule around the tool segment (or everywhere at level 0)
+    if level == 0:
+        reach_e = reach_a = np.inf
+    else:
+        reach_e = (2 * s - size.h_e) / size.g
+        reach_a = (2 * s - size.h_a) / size.g
+    if reach_e <= 0 and reach_a <= 0:
+        return np.zeros((0, 3))
+    reach = min(max(reach_e, reach_a, 0.0) + 2 * s, radius)
+    zlo = max(size.z_lo - reach, -radius)
+    zhi = min(size.z_hi + reach, radius)
+    nxy = int(np.ceil(reach / u))
+    ix = np.arange(-nxy, nxy + 1)
+    iy = np.arange(0 if half else -nxy, nxy + 1)
+    iz = np.arange(int(np.floor(zlo / u)), int(np.ceil(zhi / u)) + 1)
+    out = []
+    for parity in (0, 1):
+        ax, ay, az = ix[(ix & 1) == parity], iy[(iy & 1) == parity], iz[(iz & 1) == parity]
+        if ax.size == 0 or ay.size == 0 or az.size == 0:
+            continue
+        # chunk along z to bound memory
+        step = max(1, int(4e6 // max(1, ax.size * ay.size)))
+        for k0 in range(0, az.size, step):
+            A, B, C = np.meshgrid(ax, ay, az[k0:k0 + step], indexing="ij")
+            A, B, C = A.ravel(), B.ravel(), C.ravel()
+            if parity == 0 and level > 0:
+                # drop points already present in the coarser lattice: all = 0 mod 4 or all = 2 mod 4
+                m = (A & 3) | (B & 3) | (C & 3)
+                m2 = ((A & 3) == 2) & ((B & 3) == 2) & ((C & 3) == 2)
+                keep = ~((m == 0) | m2)
+                A, B, C = A[keep], B[keep], C[keep]
+            p = np.stack([A, B, C], axis=1) * u
+            h = size(p)
+            keep = h < 2 * s if level > 0 else np.ones(p.shape[0], bool)
+            out.append(p[keep])
+    if not out:
+        return np.zeros((0, 3))
+    p = np.concatenate(out)
+    p = p + rng.uniform(-jitter, jitter, size=p.shape) * s
+    return p
+
+
+def _plane_level_points(level, s, size, radius, rng, jitter):
+    """Nested centred-square lattice on the symmetry plane y = 0 (same nesting rule as the BCC lattice)."""
+    u = s / 2.0
+    if level == 0:
+        reach = radius
+    else:
+        r = max((2 * s - size.h_e) / size.g, (2 * s - size.h_a) / size.g)
+        if r <= 0:
+            return np.zeros((0, 3))
+        reach = min(r + 2 * s, radius)
+    zlo = max(size.z_lo - reach, -radius)
+    zhi = min(size.z_hi + reach, radius)
+    nx = int(np.ceil(reach / u))
+    ix = np.arange(-nx, nx + 1)
+    iz = np.arange(int(np.floor(zlo / u)), int(np.ceil(zhi / u)) + 1)
+    out = []
+    for parity in (0, 1):
+        A, C = np.meshgrid(ix[(ix & 1) == parity], iz[(iz & 1) == parity], indexing="ij")
+        A, C = A.ravel(), C.ravel()
+        if parity == 0 and level > 0:
+            keep = ~((((A & 3) | (C & 3)) == 0) | (((A & 3) == 2) & ((C & 3) == 2)))
+            A, C = A[keep], C[keep]
+        p = np.stack([A * u, np.zeros(A.shape[0]), C * u], axis=1)
+        if level > 0:
+            p = p[size(p) < 2 * s]
+        out.append(p)
+    p = np.concatenate(out)
+    jit = rng.uniform(-jitter, jitter, size=p.shape) * s
+    jit[:, 1] = 0.0
+    return p + jit
+
+
+def _sphere_points(radius, h, half):
+    """Fibonacci points on the (hemi)sphere + the rim circle on y = 0."""
+    n = max(16, int(4 * np.pi * radius ** 2 / (0.866 * h * h)))
+    k = np.arange(n) + 0.5
+    phi = np.arccos(1 - 2 * k / n)
+    theta = np.pi * (1 + 5 ** 0.5) * k
+    p = radius * np.stack([np.cos(theta) * np.sin(phi), np.sin(theta) * np.sin(phi), np.cos(phi)], axis=1)
+    if not half:
+        return p
+    p = p[p[:, 1] > 0.4 * h]
+    m = max(8, int(2 * np.pi * radius / h))
+    a = 2 * np.pi * (np.arange(m) + 0.5) / m
+    rim = radius * np.stack([np.cos(a), np.zeros(m), np.sin(a)], axis=1)
+    rim = rim[np.abs(rim[:, 0]) > 0.4 * h]  # the poles (0,0,+-R) come from the axis
+    return np.concatenate([p, rim])
+
+
+def half_ball_points(radius, electrodes_z, h_electrode=0.02, h_axis=0.1, h_max=None, grading=0.35, seed=0, half=True,
+                     jitter=0.08):
+    """Graded point cloud; returns (points, n_axis) with the axis points first (sorted by z)."""
+    rng = np.random.default_rng(seed)
+    h_max = h_max or radius / 8.0
+    size = SizeField(electrodes_z, h_electrode, h_axis, h_max, grading)
+    axis_z = _axis_points(size, radius)
+    axis = np.stack([np.zeros_like(axis_z), np.zeros_like(axis_z), axis_z], axis=1)
+    nlev = int(np.ceil(np.log2(h_max / min(h_electrode, h_axis)))) + 1
+    vol, pla = [], []
+    for level in range(nlev):
+        s = h_max / 2 ** level
+        p = _bcc_level_points(level, s, size, radius, rng, jitter, half)
+        if p.shape[0]:
+            h = size(p)
+            rho = np.hypot(p[:, 0], p[:, 1])
+            keep = (np.linalg.norm(p, axis=1) < radius - 0.55 * h) & (rho > 0.6 * h)
+            if half:
+                keep &= p[:, 1] > 0.45 * h
+            vol.append(p[keep])
+        if half:
+            q = _plane_level_points(level, s, size, radius, rng, jitter)
+            if q.shape[0]:
+                h = size(q)
+                keep = (np.linalg.norm(q, axis=1) < radius - 0.55 * h) & (np.abs(q[:, 0]) > 0.6 * h)
+                pla.append(q[keep])
+    sph = _sphere_points(radius, h_max, half)
+    # exactly cospherical points make one giant degenerate facet of the lifted hull (Qhull crawls):
+    # pull them inside by a relative 1e-7 at random; "on the sphere" is tested with 1e-6 below
+    sph *= 1.0 - 1e-7 * rng.uniform(0.0, 1.0, size=(sph.shape[0], 1))
+    parts = [axis] + pla + vol + [sph]
+    return np.concatenate(parts), axis.shape[0], size
+
+
+def _quality(points, elems):
+    """volume / (rms edge length)^3, normalised so the regular tet scores 1."""
+    x = points[elems]
+    vol = np.abs(np.linalg.det(x[:, 1:] - x[:, :1])) / 6.0
+    e2 = sum(((x[:, i] - x[:, j]) ** 2).sum(axis=1) for i in range(4) for j in range(i + 1, 4)) / 6.0
+    return vol / (e2 ** 1.5) * (6.0 * np.sqrt(2.0))
+
+
+def half_ball_mesh(radius, electrodes_z, material=None, **kw):
+    """Graded half-ball (or full ball with half=False) tet mesh.
+
+    Returns dict(points, elems, mat, bfacets, bc, bc_names, n_axis); vertices are renumbered along a
+    Morton curve for memory locality with the axis vertices kept as mesh vertices.  `material(centroids)`
+    -> 0-based material index per tet (default: all 0)."""
+    from scipy.spatial import Delaunay
+
+    half = kw.get("half", True)
+    pts, n_axis, _ = half_ball_points(radius, electrodes_z, **kw)
+    # Morton order (locality of vertex numbers -> locality of CSR columns)
+    q = np.clip(((pts + radius) / (2 * radius) * 1023).astype(np.int64), 0, 1023)
+
+    def spread(v):
+        v = (v | (v << 16)) & 0x030000FF
+        v = (v | (v << 8)) & 0x0300F00F
+        v = (v | (v << 4)) & 0x030C30C3
+        v = (v | (v << 2)) & 0x09249249
+        return v
+
+    code = spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+    pts = pts[np.argsort(code, kind="stable")]
+    # Qhull is ~10x slower with thousands of exactly coplanar hull points (the symmetry plane):
+    # triangulate a copy whose plane points are lifted by <= 2e-11 R, keep the exact coordinates;
+    # the flat tets this creates on the plane are boundary slivers and are peeled below
+    lifted = pts.copy()
+    on_plane = lifted[:, 1] == 0.0
+    lifted[on_plane, 1] += np.random.default_rng(kw.get("seed", 0) + 1).uniform(0.0, 2e-11 * radius, size=int(on_plane.sum()))
+    tri = Delaunay(lifted)
+    elems = tri.simplices.astype(np.int32)
+    elems = elems[~on_plane[elems].all(axis=1)]  # exactly flat tets lying in the symmetry plane
+    # peel boundary slivers (flat tets between nearly coplanar hull points)
+    for _ in range(6):
+        qual = _quality(pts, elems)
+        _, owner = boundary_facets(elems, return_owner=True)
+        drop = np.zeros(elems.shape[0], bool)
+        drop[owner] = True  # tets that own a boundary face ...
+        drop &= qual < 2e-2  # ... and are slivers
+        if not drop.any():
+            break
+        elems = elems[~drop]
+    # positive orientation
+    x = pts[elems]
+    neg = np.linalg.det(x[:, 1:] - x[:, :1]) < 0
+    elems[neg] = elems[neg][:, [0, 2, 1, 3]]
+    # drop unused vertices (none expected) and build boundary
+    used = np.zeros(pts.shape[0], bool)
+    used[elems.ravel()] = True
+    if not used.all():
+        remap = np.cumsum(used) - 1
+        pts = pts[used]
+        elems = remap[elems].astype(np.int32)
+    bfacets = boundary_facets(elems)
+    rr = np.linalg.norm(pts, axis=1)
+    on_sphere = rr >= radius * (1 - 1e-6)
+    bc = np.where(on_sphere[bfacets].all(axis=1), 2, 1).astype(np.int32)
+    cen = pts[elems].mean(axis=1)
+    mat = np.zeros(elems.shape[0], np.int32) if material is None else np.asarray(material(cen), dtype=np.int32)
+    return {"points": pts, "elems": elems, "mat": mat, "bfacets": bfacets, "bc": bc,
+            "bc_names": ["symmetry_plane", "dirichlet_boundary"], "half": half}
+
+
+# ----------------------------------------------------------------------------------------------
+# material predicates
+# ----------------------------------------------------------------------------------------------
+def layered_material(layer_tops, dip_rad=0.0, borehole_radius=0.1, invasion=None, inclusion=None):
+    """Centroid -> material index following the reference's order (`gmsh_functions.py:592-624`):
+    0 borehole; then per layer (top->bottom): flushed zone if the layer has one, undisturbed zone.
+    `layer_tops`: ascending interface depths z_1..z_{n-1} on the axis (n layers);
+    `invasion`: per-layer flushed-zone radius or None/NaN; dipping planes z = z_i + tan(dip) x;
+    `inclusion`: (centre xyz, radius) gets its own material index appended at the end."""
+    tops = np.asarray(layer_tops, dtype=float)
+    nl = tops.shape[0] + 1
+    inv = [None] * nl if invasion is None else list(invasion)
+    ids, nxt = [], 1
+    for i in range(nl):
+        has = inv[i] is not None and inv[i] == inv[i]
+        fz = nxt if has else -1
+        nxt += 1 if has else 0
+        ids.append((fz, nxt))
+        nxt += 1
+    n_materials = nxt + (1 if inclusion is not None else 0)
+
+    def fn(c):
+        rho = np.hypot(c[:, 0], c[:, 1])
+        zeff = c[:, 2] - np.tan(dip_rad) * c[:, 0]
+        layer = np.searchsorted(tops, zeff)
+        m = np.empty(c.shape[0], np.int32)
+        for i, (fz, uz) in enumerate(ids):
+            sel = layer == i
+            if fz >= 0:
+                m[sel] = np.where(rho[sel] < inv[i], fz, uz)
+            else:
+                m[sel] = uz
+        if inclusion is not None:
+            cen, rad = inclusion
+            m[np.linalg.norm(c - np.asarray(cen), axis=1) < rad] = nxt
+        m[rho < borehole_radius] = 0
+        return m
+
+    fn.n_materials = n_materials
+    return fn

@@ -1,0 +1,42 @@
+"""Shared mesh / task fixtures for the parity tests (seeded, small enough for the oracle)."""
+import numpy as np
+
+from remo3d_b200 import meshgen, planner, tools as tl
+from remo3d_b200.mesh import Mesh
+
+SIX_TOOLS = ["B5.7A0.4M", "B4.48A1.62M", "M1.0A0.1B", "A2.0M0.5N", "N0.5M2.0A", "M4.0A0.5B"]
+
+
+def box_case(n=3):
+    """Unit-ish box, axis = edge x=y=0, z in [-1,1]; Dirichlet on the far faces x=1, y=1 and the ends z=+-1."""
+    pts, elems, bf, bc = meshgen.box_mesh(n, dirichlet=lambda c: (c[:, 0] > 1 - 1e-9) | (c[:, 1] > 1 - 1e-9) | (np.abs(c[:, 2]) > 1 - 1e-9))
+    cen = pts[elems].mean(axis=1)
+    mat = (cen[:, 2] > 0).astype(np.int32) + (cen[:, 0] > 0.5).astype(np.int32)
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(pts.shape[0])  # scramble vertex numbers: exercises the sorting of element vertices
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.shape[0])
+    pts = pts[perm]
+    elems = inv[elems].astype(np.int32)
+    bf = inv[bf].astype(np.int32)
+    mesh = Mesh(pts, elems, mat, bf, bc, ["natural", "dirichlet_boundary"])
+    return mesh, [1.0, 0.25, 3.0]
+
+
+def ball_case(h_electrode=0.08, h_axis=0.3, grading=0.5, tools=("A2.0M0.5N", "N0.5M2.0A", "B5.7A0.4M"), depths=(10.0, 10.1, 10.2),
+              batch_size=5, layered=True, fsec=True, radius=50.0, seed=0):
+    """Graded half-ball around the first task of a small plan; returns (mesh, sigma, flat task, tools params)."""
+    params, sec = tl.set_tools_parameters(list(tools), fsec)
+    _, tasks = planner.prepare_simulation_depths_and_tasks(params, sec, np.asarray(depths, dtype=float), batch_size)
+    task = tasks[0]
+    ez = task[1][0]
+    if layered:
+        material = meshgen.layered_material([-1.0, 1.5], dip_rad=np.deg2rad(30.0), borehole_radius=0.1, invasion=[None, 0.4, None],
+                                            inclusion=((3.0, 2.0, 1.0), 1.5))
+        sigma = [1 / 1.0, 1 / 10.0, 1 / 5.0, 1 / 100.0, 1 / 10.0, 1 / 2.0]
+    else:
+        material, sigma = None, [1 / 10.0]
+    m = meshgen.half_ball_mesh(radius, ez, material=material, h_electrode=h_electrode, h_axis=h_axis, grading=grading, seed=seed)
+    mesh = Mesh(m["points"], m["elems"], m["mat"], m["bfacets"], m["bc"], m["bc_names"])
+    flat = planner.flatten_task(task, params, three_d=True)
+    return mesh, sigma, flat, params

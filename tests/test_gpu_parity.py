@@ -1,0 +1,156 @@
+"""GPU parity: the CUDA path through the C ABI against the CPU oracle on identical meshes.
+
+Bars (BASELINE.json north_star): mesh/DOF numbering and CSR pattern bit-exact; assembled matrix <= 1e-12 relative
+Frobenius; electrode potentials and apparent resistivity <= 1e-6 relative at CG relative residual 1e-10."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import fem_oracle as fo
+from remo3d_b200 import _cabi
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = _cabi.Context(0)
+    yield c
+    c.close()
+
+
+def _setup(ctx, mesh, order, dirichlet="dirichlet_boundary"):
+    flags = mesh.dirichlet_flags(dirichlet)
+    ctx.mesh_set(mesh.dim, mesh.points, mesh.elems, mesh.mat, mesh.bfacets, flags, mesh.axis_vertices())
+    ctx.space_build(order)
+    return flags
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("case", ["box", "ball"])
+def test_numbering_pattern_matrix(ctx, order, case):
+    if case == "box":
+        mesh, sigma = helpers.box_case(3)
+    else:
+        mesh, sigma, _, _ = helpers.ball_case()
+    flags = _setup(ctx, mesh, order)
+    space = fo.Space(mesh.nv, mesh.elems, order, 3)
+    assert ctx.ndof == space.ndof and ctx.ne == space.ne
+    edges, faces, ee, ef = ctx.topology()
+    np.testing.assert_array_equal(edges, space.edges)
+    np.testing.assert_array_equal(ee, space.elem_edges)
+    if order == 3:
+        assert ctx.nf == space.nf
+        np.testing.assert_array_equal(faces, space.faces)
+        np.testing.assert_array_equal(ef, space.elem_faces)
+    np.testing.assert_array_equal(ctx.dirichlet(), space.dirichlet_dofs(mesh.bfacets, flags))
+
+    ctx.assemble(sigma)
+    rowptr, col, val = ctx.matrix()
+    A = fo.assemble(mesh.points, space, sigma, mesh.mat)
+    assert ctx.nnz == A.nnz
+    np.testing.assert_array_equal(rowptr, A.indptr)
+    np.testing.assert_array_equal(col, A.indices)
+    err = np.linalg.norm(val - A.data) / np.linalg.norm(A.data)
+    assert err <= 1e-12, err
+    # structural properties of a stiffness matrix: symmetric, zero row sums on the vertex block
+    G = sp.csr_matrix((val, col, rowptr), shape=(ctx.ndof, ctx.ndof))
+    assert abs(G - G.T).max() <= 1e-12 * abs(G).max()
+    ones = np.zeros(ctx.ndof)
+    ones[: mesh.nv] = 1.0  # the constant function in the hierarchical basis
+    assert np.abs(G @ ones).max() <= 1e-10 * abs(G).max()
+
+
+def test_assembly_is_bit_reproducible(ctx):
+    mesh, sigma, _, _ = helpers.ball_case()
+    _setup(ctx, mesh, 2)
+    ctx.assemble(sigma)
+    v1 = ctx.matrix()[2].copy()
+    ctx.assemble(sigma)
+    v2 = ctx.matrix()[2]
+    assert np.array_equal(v1, v2)
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_solve_matches_oracle(ctx, order):
+    mesh, sigma, flat, _ = helpers.ball_case()
+    ref = fo.solve_task(mesh.points, mesh.elems, mesh.mat, sigma, mesh.bfacets, mesh.dirichlet_flags("dirichlet_boundary"), order, flat)
+    _setup(ctx, mesh, order)
+    ctx.assemble(sigma)
+    ctx.precond_setup("local")
+    ctx.rhs_point_sources(flat["src_ptr"], flat["src_z"], flat["src_fac"])
+    nrhs = flat["src_ptr"].shape[0] - 1
+    axis = ref["axis"]
+    for r in range(nrhs):
+        lo, hi = flat["src_ptr"][r], flat["src_ptr"][r + 1]
+        f = fo.point_source_rhs(axis, ctx.ndof, flat["src_z"][lo:hi], flat["src_fac"][lo:hi])
+        np.testing.assert_allclose(ctx.rhs(r), f, rtol=0, atol=1e-15)
+    iters, relres = ctx.solve(rtol=1e-10, maxit=20000)
+    assert (relres <= 1e-10).all() and (iters > 0).all()
+    # potentials at every electrode of the task
+    zs = np.unique(np.concatenate([flat["pt_z0"], flat["pt_z1"][~np.isnan(flat["pt_z1"])]]))
+    for r in range(nrhs):
+        u_gpu = ctx.sample_axis(zs, np.full(zs.shape, r))
+        u_ref = np.array([fo.sample_axis(axis, ref["U"][:, r], z) for z in zs])
+        np.testing.assert_allclose(u_gpu, u_ref, rtol=1e-6)
+        # the whole solution vector, relative to its norm
+        u = ctx.solution(r)
+        assert np.linalg.norm(u - ref["U"][:, r]) <= 1e-6 * np.linalg.norm(ref["U"][:, r])
+    ra = ctx.apparent_resistivity(flat["pt_rhs"], flat["pt_z0"], flat["pt_z1"], flat["pt_k"], flat["scale"])
+    np.testing.assert_allclose(ra, ref["ra"], rtol=1e-6)
+
+
+def test_homogeneous_ball_gives_rho(ctx):
+    """Known answer: homogeneous medium -> Ra == rho for every tool, up to discretisation error."""
+    mesh, sigma, flat, _ = helpers.ball_case(h_electrode=0.03, h_axis=0.12, grading=0.4, layered=False)
+    _setup(ctx, mesh, 2)
+    ctx.assemble(sigma)
+    ctx.precond_setup("local")
+    ctx.rhs_point_sources(flat["src_ptr"], flat["src_z"], flat["src_fac"])
+    ctx.solve(rtol=1e-10, maxit=20000)
+    ra = ctx.apparent_resistivity(flat["pt_rhs"], flat["pt_z0"], flat["pt_z1"], flat["pt_k"], flat["scale"])
+    np.testing.assert_allclose(ra, 10.0, rtol=5e-3)
+
+
+def test_two_current_electrodes_and_edge_sources(ctx):
+    """+1/-1 source pairs (force_single_electrode_configuration=False) and electrodes that fall inside axis edges."""
+    mesh, sigma, flat, _ = helpers.ball_case(tools=("A0.2B3.0M", "N1.0A0.5B"), fsec=False, depths=(10.0, 10.1), batch_size=4)
+    # shift every electrode by 1 mm: none is a mesh vertex any more -> edge shape functions are exercised
+    for key in ("src_z", "pt_z0", "pt_z1"):
+        flat[key] = flat[key] + 1e-3
+    for order in (2, 3):
+        ref = fo.solve_task(mesh.points, mesh.elems, mesh.mat, sigma, mesh.bfacets, mesh.dirichlet_flags("dirichlet_boundary"), order, flat)
+        _setup(ctx, mesh, order)
+        ctx.assemble(sigma)
+        ctx.precond_setup("local")
+        ctx.rhs_point_sources(flat["src_ptr"], flat["src_z"], flat["src_fac"])
+        ctx.solve(rtol=1e-10, maxit=20000)
+        ra = ctx.apparent_resistivity(flat["pt_rhs"], flat["pt_z0"], flat["pt_z1"], flat["pt_k"], flat["scale"])
+        np.testing.assert_allclose(ra, ref["ra"], rtol=1e-6)
+        assert np.isnan(flat["pt_z1"]).all()  # single potential electrode branch of worker.py:120-131
+
+
+def test_error_paths(ctx):
+    mesh, sigma = helpers.box_case(2)
+    with pytest.raises(_cabi.RemoError):
+        _cabi.Context(99)
+    _setup(ctx, mesh, 1)
+    with pytest.raises(_cabi.RemoError) as e:
+        ctx.assemble([1.0])  # material index 2 outside the sigma list
+    assert e.value.code == _cabi.ERR_ARG
+    ctx.assemble(sigma)
+    with pytest.raises(_cabi.RemoError) as e:
+        ctx.solve()
+    assert e.value.code == _cabi.ERR_STATE
+    ctx.precond_setup("local")
+    with pytest.raises(_cabi.RemoError) as e:
+        ctx.rhs_point_sources([0, 1], [5.0], [1.0])  # outside the axis
+    assert e.value.code == _cabi.ERR_MESH
+    with pytest.raises(_cabi.RemoError):
+        ctx.space_build(4)
+    ctx.rhs_point_sources([0, 1], [0.0], [1.0])
+    ctx.precond_setup("local") if False else None
+    with pytest.raises(_cabi.RemoError) as e:
+        ctx.solve(rtol=1e-14, maxit=2)
+    assert e.value.code == _cabi.ERR_NOCONV
