@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- log points / second of the ReMo3D forward-solve hot path on B200.
+
+A *step* is one pass of the hot path over one mesh task (workload C4):
+    upload mesh -> symbolic phase (H1 order-2 space, CSR pattern) -> numeric assembly ->
+    preconditioner setup -> point-source right-hand sides -> multi-RHS PCG to 1e-10 ->
+    axis sampling -> apparent resistivity of every log point of the task.
+The mesh is the synthetic 3D dipping-bed + inclusion model (half-ball R = 50 m, graded to the
+electrodes, seed 0) sized to ~5 M degrees of freedom at order 2; the task is one batch of the
+planner (batch_size 5 sources, the 4 tools of config C5) and yields `points_per_step` log points.
+
+  value : whole-job log points/s with the mesh arrays already resident in HBM (CUDA tensors)
+  e2e   : the same through the public API with HOST (pinned) mesh arrays and the result read back
+          to the host every step (h2d / d2h inside the timed region)
+  --impl reference : the CPU restatement of the reference path (oracle/, NumPy/SciPy; NGSolve itself is
+          not installable) farmed over all host cores on a bounded sample of the workload.
+
+Launch: `python bench.py --gpus 1 --steps K --warmup W`, or under torchrun with one rank per GPU
+(points are sharded over ranks, no collective in the data path; timing = max over ranks).
+"""
+import argparse
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TOOLS = ["A2.0M0.5N", "N0.5M2.0A", "B5.7A0.4M", "M4.0A0.5B"]
+SIGMA = [1 / 1.0, 1 / 10.0, 1 / 100.0, 1 / 10.0, 1 / 2.0]       # mud, 10/100/10 ohm-m beds, inclusion
+SIZES = {
+    # name: (h_electrode, h_axis, grading, h_max)  -> dofs at order 2
+    "5M": (0.008, 0.0222, 0.125, 4.0),
+    "1M": (0.01, 0.04, 0.19, 5.0),
+    "200k": (0.03, 0.1, 0.33, 6.0),
+    "60k": (0.06, 0.25, 0.5, 6.0),
+}
+
+
+def make_task():
+    from remo3d_b200 import planner, tools as tl
+
+    params, sec = tl.set_tools_parameters(TOOLS)
+    _, tasks = planner.prepare_simulation_depths_and_tasks(params, sec, np.arange(0, 100, 0.1), 5)
+    task = tasks[len(tasks) // 2]
+    return task, planner.flatten_task(task, params, three_d=True)
+
+
+def make_mesh(size, task, log=lambda *a: None):
+    """Synthetic C4 mesh (cached under the system temp dir: all ranks and both arms share it)."""
+    from remo3d_b200 import meshgen
+
+    he, ha, g, hm = SIZES[size]
+    key = hashlib.sha1(repr((size, he, ha, g, hm, task[1][0].tolist(), 3)).encode()).hexdigest()[:12]
+    path = os.path.join(tempfile.gettempdir(), "remo3d_bench_mesh_%s.npz" % key)
+    if os.path.exists(path):
+        z = np.load(path)
+        return {k: z[k] for k in z.files}
+    t0 = time.time()
+    material = meshgen.layered_material([-1.0, 1.5], dip_rad=np.deg2rad(30.0), borehole_radius=0.1, inclusion=((3.0, 2.0, 1.0), 1.5))
+    m = meshgen.half_ball_mesh(50.0, task[1][0], material=material, h_electrode=he, h_axis=ha, grading=g, h_max=hm, seed=0)
+    from remo3d_b200.mesh import Mesh
+
+    mesh = Mesh(m["points"], m["elems"], m["mat"], m["bfacets"], m["bc"], m["bc_names"])
+    out = {"points": mesh.points, "elems": mesh.elems, "mat": mesh.mat, "bfacets": mesh.bfacets,
+           "bdir": mesh.dirichlet_flags("dirichlet_boundary"), "axis": mesh.axis_vertices()}
+    tmp = path + ".%d.tmp.npz" % os.getpid()
+    np.savez(tmp, **out)
+    os.replace(tmp, path)
+    log("mesh %s generated in %.1f s: %d vertices, %d tets" % (size, time.time() - t0, mesh.nv, mesh.ne))
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200", "-i", str(index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def spmm_bytes(nnz, ndof, k):
+    """Algorithmic bytes of one SpMM launch: fp64 values + int32 columns, int64 row pointers, P read once,
+    Q written once: 12 nnz + N (8 + 16 k)."""
+    return 12.0 * nnz + ndof * (8.0 + 16.0 * k)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from remo3d_b200 import _cabi
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; this arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    log = (lambda *a: print(*a, file=sys.stderr, flush=True)) if rank == 0 else (lambda *a: None)
+
+    task, flat = make_task()
+    if rank == 0:
+        m = make_mesh(args.size, task, log)
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        m = make_mesh(args.size, task)
+
+    stream = torch.cuda.Stream()
+    ctx = _cabi.Context(local)
+    ctx.set_stream(stream.cuda_stream)
+    names = ["points", "elems", "mat", "bfacets", "bdir", "axis"]
+    host = {k: torch.from_numpy(np.ascontiguousarray(m[k])).pin_memory() for k in names}
+    dev = {k: host[k].cuda() for k in names}
+    npts = flat["pt_rhs"].shape[0]
+    nrhs = flat["src_ptr"].shape[0] - 1
+    ra_host = torch.empty(npts, dtype=torch.float64).pin_memory()
+    ra_np = ra_host.numpy()
+    info = {}
+
+    def step(a):
+        ctx.mesh_set(3, a["points"], a["elems"], a["mat"], a["bfacets"], a["bdir"], a["axis"])
+        ctx.space_build(args.order)
+        ctx.assemble(SIGMA)
+        ctx.precond_setup(args.preconditioner)
+        ctx.rhs_point_sources(flat["src_ptr"], flat["src_z"], flat["src_fac"])
+        it, rel = ctx.solve(rtol=1e-10, maxit=args.maxit)
+        ctx.apparent_resistivity(flat["pt_rhs"], flat["pt_z0"], flat["pt_z1"], flat["pt_k"], flat["scale"], out=ra_np)
+        info.update(iters=it.tolist(), relres=float(rel.max()))
+
+    def timed(a, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step(a)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step(dev)
+    torch.cuda.synchronize()
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ctx.profile(True)
+    ms_dev = timed(dev, args.steps)
+    spmm_ms, spmm_n = ctx.profile_get()
+    ctx.profile(False)
+    launches = ctx.launch_count() - launches0
+    stage = ctx.stage_times()
+    ms_e2e = timed(host, args.steps)
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        ndof, nnz = ctx.ndof, ctx.nnz
+        total_pts = npts * args.steps * world
+        value = total_pts / (ms_dev / 1e3)
+        e2e = total_pts / (ms_e2e / 1e3)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        per_launch = spmm_ms / max(spmm_n, 1) / 1e3
+        achieved = spmm_bytes(nnz, ndof, nrhs) / per_launch / 1e9 if spmm_n else 0.0
+        h2d = sum(host[k].numel() * host[k].element_size() for k in names) + flat["src_z"].nbytes * 2 + flat["src_ptr"].nbytes \
+            + flat["pt_rhs"].nbytes + 3 * flat["pt_z0"].nbytes + len(SIGMA) * 8
+        line = {
+            "metric": "log points/sec", "value": value, "unit": "log points/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": "C4: synthetic 3D dipping-bed (30 deg, 10/100/10 ohm-m) + spherical inclusion, half-ball R=50 m, "
+                            "order-%d H1, one mesh task per step (batch_size 5, 4 tools), size %s" % (args.order, args.size),
+                "ndof": ndof, "nnz": nnz, "nnz_per_row": nnz / ndof, "vertices": int(m["points"].shape[0]), "tets": int(m["elems"].shape[0]),
+                "nrhs": nrhs, "points_per_step": npts, "solves_per_step": nrhs, "preconditioner": args.preconditioner,
+                "rtol": 1e-10, "iterations": info.get("iters"), "max_relres": info.get("relres"),
+                "l2": "inputs larger than L2 (matrix %.0f MB + vectors %.0f MB vs 126 MB L2); no explicit flush" % (12e-6 * nnz, 48e-6 * ndof * nrhs),
+                "sharding": "independent mesh tasks per rank, no data-path collective", "stage_ms": stage,
+            },
+            "e2e": {"value": e2e, "unit": "log points/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(npts * 8),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_spmm (PCG SpMM + fused p.q)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                         "bytes_per_launch": spmm_bytes(nnz, ndof, nrhs), "avg_launch_ms": per_launch * 1e3, "launches_timed": int(spmm_n),
+                         "frac_of_8TBs_spec": achieved / 8000.0, "spmm_share_of_step": spmm_ms / ms_dev},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, log)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (NumPy/SciPy restatement of the reference path) farmed over the host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_task(payload):
+    from oracle import fem_oracle as fo
+
+    m, flat, order = payload
+    t0 = time.time()
+    res = fo.solve_task(m["points"], m["elems"], m["mat"], SIGMA, m["bfacets"], m["bdir"].astype(bool), order, flat, solver="pcg")
+    return time.time() - t0, res["ra"].tolist(), res["space"].ndof
+
+
+def cpu_farm(size, order, steps, workers):
+    """`steps` rounds; in each round every worker solves one mesh task (the reference's MPI farm, remo3d.py:843-860)."""
+    import multiprocessing as mp
+
+    task, flat = make_task()
+    m = make_mesh(size, task)
+    npts = flat["pt_rhs"].shape[0]
+    ctxm = mp.get_context("fork")
+    with ctxm.Pool(workers) as pool:
+        t0 = time.time()
+        ndof = 0
+        for _ in range(steps):
+            out = pool.map(_cpu_task, [(m, flat, order)] * workers)
+            ndof = out[0][2]
+        wall = time.time() - t0
+    return {"value": npts * workers * steps / wall, "wall_s": wall, "ndof": ndof, "points": npts * workers * steps}
+
+
+def cpu_baseline(args, log):
+    workers = os.cpu_count() or 1
+    r = cpu_farm(args.cpu_size, args.order, 1, workers)
+    log("cpu baseline: %d workers, %.1f s" % (workers, r["wall_s"]))
+    return {"value": r["value"], "unit": "log points/s", "cores": workers, "kind": "port",
+            "sample": "oracle/fem_oracle.py (NumPy/SciPy restatement, Jacobi-PCG to 1e-13) on the same generator at size %s "
+                      "(%d dofs, order %d) instead of %s; %d worker processes x 1 task each, %.1f s wall" % (args.cpu_size, r["ndof"], args.order, args.size, workers, r["wall_s"])}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if rank != 0:
+        return
+    workers = os.cpu_count() or 1
+    for _ in range(args.warmup and 0):  # the CPU arm has no cache or JIT state to warm
+        pass
+    r = cpu_farm(args.cpu_size, args.order, max(1, args.steps), workers)
+    sample = ("CPU restatement of the reference path (oracle/fem_oracle.py; NGSolve is not installable here) on a bounded sample: "
+              "generator of workload C4 at size %s (%d dofs, order %d), %d worker processes x %d rounds" % (args.cpu_size, r["ndof"], args.order, workers, max(1, args.steps)))
+    line = {"impl": "reference", "metric": "log points/sec", "value": r["value"], "unit": "log points/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["wall_s"] * 1e3 / max(1, args.steps), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C4 bounded sample: size %s, order %d" % (args.cpu_size, args.order), "ndof": r["ndof"]},
+            "cpu_baseline": {"value": r["value"], "unit": "log points/s", "cores": workers, "kind": "port", "sample": sample},
+            "e2e": {"value": r["value"], "unit": "log points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", default="5M", choices=list(SIZES))
+    ap.add_argument("--cpu-size", default="60k", choices=list(SIZES))
+    ap.add_argument("--order", type=int, default=2)
+    ap.add_argument("--preconditioner", default="multigrid", choices=["local", "multigrid"])
+    ap.add_argument("--maxit", type=int, default=20000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

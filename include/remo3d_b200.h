@@ -47,6 +47,10 @@ extern "C" {
 int remo_ctx_create(int device, void** ctx);
 int remo_ctx_destroy(void* ctx);
 const char* remo_last_error(void* ctx);
+/* Run all further work of this context on a caller-owned CUDA stream (a `cudaStream_t`, e.g.
+ * `torch.cuda.Stream().cuda_stream`), so the caller can bracket calls with its own CUDA events.
+ * The stream must outlive the context and must not be the legacy default stream 0.            */
+int remo_ctx_set_stream(void* ctx, void* stream);
 
 /* Upload one mesh (replaces `ngs.Mesh(mesh)`, workers/worker.py:100).
  *   dim          2 (axisymmetric r,z triangles) or 3 (tets)

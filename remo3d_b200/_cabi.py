@@ -22,6 +22,7 @@ SIGNATURES = {
     "remo_ctx_create": (C.c_int, [C.c_int, C.POINTER(_p)]),
     "remo_ctx_destroy": (C.c_int, [_p]),
     "remo_last_error": (C.c_char_p, [_p]),
+    "remo_ctx_set_stream": (C.c_int, [_p, _p]),
     "remo_mesh_set": (C.c_int, [_p, C.c_int, C.c_int64, _p, C.c_int64, _p, _p, C.c_int64, _p, _p, C.c_int64, _p]),
     "remo_space_build": (C.c_int, [_p, C.c_int, _i64p, _i64p, _i64p, _i64p]),
     "remo_topology_get": (C.c_int, [_p, _p, _p, _p, _p]),
@@ -102,6 +103,10 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def set_stream(self, cuda_stream_handle):
+        """Adopt a caller-owned stream (int handle, e.g. torch.cuda.Stream().cuda_stream)."""
+        self._ck(self.lib.remo_ctx_set_stream(self.h, C.c_void_p(int(cuda_stream_handle))))
 
     def _ck(self, rc, allow=()):
         if rc != OK and rc not in allow:

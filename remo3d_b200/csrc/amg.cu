@@ -1,0 +1,485 @@
+// "multigrid" preconditioner (REMO_PRECOND_MULTIGRID): two-level hierarchical-basis splitting with an
+// aggregation-AMG V-cycle on the P1 block.
+//
+// Reference behaviour being replaced: `c = ngs.Preconditioner(a, "multigrid")`
+// (/root/reference/remo3d/ngsolve_functions.py:46, default of remo3d.py:82).  On a single-level mesh NGSolve's
+// multigrid is a two-level method: exact solve of the lowest-order (P1) problem + smoothing of the high-order
+// dofs [NGS, SURVEY 8a-a4].  Here:
+//   * the dofs are [vertices | edges | faces] in a HIERARCHICAL basis, so the P1 stiffness matrix is literally the
+//     leading nv x nv block of A (no second assembly, prolongation = injection);
+//   * z = M r :  z_high = D^-1 r_high  (Jacobi on the edge / face dofs, whose block is well conditioned), and
+//                z_vert = V-cycle(A_vv) r_vert;
+//   * the V-cycle hierarchy is built on the GPU by plain aggregation: vertices are ranked along a Morton curve of
+//     their coordinates and every 8 consecutive ranks form an aggregate (coarse levels: 8 consecutive rows), the
+//     coarse operators are Galerkin products with piecewise-constant prolongation (sort + reduce-by-key), the
+//     coarsest level (<= 256 rows) is inverted densely.  Smoother: damped Jacobi, symmetric cycle -> M is SPD and
+//     plain PCG applies.
+// Everything works on row-major n x nrhs blocks, like the PCG.
+#include <cub/cub.cuh>
+
+#include <cstdlib>
+
+#include "space_view.cuh"
+
+namespace {
+
+constexpr int TB = 256;
+constexpr int AGG = 8;
+constexpr int COARSEST = 256;
+constexpr int MAXLEV = 12;
+
+double env_d(const char* name, double def) {
+  const char* e = getenv(name);
+  return e ? atof(e) : def;
+}
+
+// ---------------------------------------------------------------- level 0 = free-free part of the vertex block
+__global__ void k_vv_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                           const uint8_t* __restrict__ con, int64_t nv, int32_t* __restrict__ cnt) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nv) return;
+  int n = 0;
+  const bool ci = con[i];
+  for (int64_t j = rowptr[i]; j < rowptr[i + 1]; j++) {
+    const int32_t c = col[j];
+    if (c >= nv) break;  // columns ascending: vertex dofs first
+    if (c == i || (!ci && !con[c])) n++;
+  }
+  cnt[i] = n;
+}
+
+__global__ void k_vv_fill(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
+                          const uint8_t* __restrict__ con, int64_t nv, const int64_t* __restrict__ rp0,
+                          int32_t* __restrict__ col0, double* __restrict__ val0) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nv) return;
+  int64_t o = rp0[i];
+  const bool ci = con[i];
+  for (int64_t j = rowptr[i]; j < rowptr[i + 1]; j++) {
+    const int32_t c = col[j];
+    if (c >= nv) break;
+    if (c == i || (!ci && !con[c])) { col0[o] = c; val0[o] = val[j]; o++; }
+  }
+}
+
+__global__ void k_excl_to_ptr(const int32_t* __restrict__ incl, int64_t n, int64_t* __restrict__ ptr) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i > n) return;
+  ptr[i] = (i == 0) ? 0 : (int64_t)incl[i - 1];
+}
+
+__global__ void k_level_dinv(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
+                             const uint8_t* __restrict__ con, int64_t n, double* __restrict__ dinv) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double d = 0.0;
+  if (!(con && con[i]))
+    for (int64_t j = rowptr[i]; j < rowptr[i + 1]; j++)
+      if (col[j] == (int32_t)i) d = val[j];
+  dinv[i] = d > 0.0 ? 1.0 / d : 0.0;
+}
+
+// ---------------------------------------------------------------- Morton ranks of the vertices
+__device__ __forceinline__ uint64_t spread21(uint64_t v) {
+  v &= 0x1fffffull;
+  v = (v | (v << 32)) & 0x1f00000000ffffull;
+  v = (v | (v << 16)) & 0x1f0000ff0000ffull;
+  v = (v | (v << 8)) & 0x100f00f00f00f00full;
+  v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+  v = (v | (v << 2)) & 0x1249249249249249ull;
+  return v;
+}
+
+__global__ void k_bbox(const double* __restrict__ xyz, int64_t nv, int dim, double* __restrict__ lohi) {
+  // one block; lohi[0..2] = min, [3..5] = max
+  __shared__ double smin[3][TB], smax[3][TB];
+  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+  for (int64_t i = threadIdx.x; i < nv; i += blockDim.x)
+    for (int d = 0; d < dim; d++) {
+      const double v = xyz[i * dim + d];
+      mn[d] = fmin(mn[d], v);
+      mx[d] = fmax(mx[d], v);
+    }
+  for (int d = 0; d < 3; d++) { smin[d][threadIdx.x] = mn[d]; smax[d][threadIdx.x] = mx[d]; }
+  __syncthreads();
+  for (int s = TB / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s)
+      for (int d = 0; d < 3; d++) {
+        smin[d][threadIdx.x] = fmin(smin[d][threadIdx.x], smin[d][threadIdx.x + s]);
+        smax[d][threadIdx.x] = fmax(smax[d][threadIdx.x], smax[d][threadIdx.x + s]);
+      }
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) { lohi[threadIdx.x] = smin[threadIdx.x][0]; lohi[3 + threadIdx.x] = smax[threadIdx.x][0]; }
+}
+
+__global__ void k_morton(const double* __restrict__ xyz, int64_t nv, int dim, const double* __restrict__ lohi,
+                         uint64_t* __restrict__ code, uint32_t* __restrict__ idx) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nv) return;
+  uint64_t c = 0;
+  for (int d = 0; d < dim; d++) {
+    const double ext = lohi[3 + d] - lohi[d];
+    const double t = ext > 0 ? (xyz[i * dim + d] - lohi[d]) / ext : 0.0;
+    const uint64_t q = (uint64_t)fmin(fmax(t * 2097151.0, 0.0), 2097151.0);
+    c |= spread21(q) << d;
+  }
+  code[i] = c;
+  idx[i] = (uint32_t)i;
+}
+
+// perm = vertices in Morton order -> aggregate of vertex perm[p] is p / AGG; members row-major (AGG per aggregate)
+__global__ void k_agg_from_perm(const uint32_t* __restrict__ perm, int64_t n, int32_t* __restrict__ agg, int32_t* __restrict__ members,
+                                int64_t npad) {
+  int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= npad) return;
+  if (p < n) {
+    agg[perm[p]] = (int32_t)(p / AGG);
+    members[p] = (int32_t)perm[p];
+  } else {
+    members[p] = -1;
+  }
+}
+
+// ---------------------------------------------------------------- Galerkin coarse operator, piecewise-constant P
+__global__ void k_galerkin_pairs(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
+                                 const int32_t* __restrict__ agg, const double* __restrict__ dinv, int64_t n,
+                                 uint64_t* __restrict__ keys, double* __restrict__ vals) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t ai = agg ? (uint64_t)agg[i] : (uint64_t)(i / AGG);
+  const bool dead_i = dinv[i] == 0.0;  // constrained or empty row: not part of the coarse space
+  for (int64_t j = rowptr[i]; j < rowptr[i + 1]; j++) {
+    const int32_t c = col[j];
+    const bool dead = dead_i || dinv[c] == 0.0;
+    const uint64_t ac = agg ? (uint64_t)agg[c] : (uint64_t)(c / AGG);
+    keys[j] = dead ? ~0ull : ((ai << 32) | ac);
+    vals[j] = dead ? 0.0 : val[j];
+  }
+}
+
+__global__ void k_coarse_rowptr(const uint64_t* __restrict__ ukeys, int64_t nruns, int64_t nc, int64_t* __restrict__ rowptr) {
+  int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (a > nc) return;
+  rowptr[a] = lower_bound_u64(ukeys, nruns, (uint64_t)a << 32);
+}
+
+__global__ void k_coarse_cols(const uint64_t* __restrict__ ukeys, int64_t nnz, int32_t* __restrict__ col) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < nnz) col[i] = (int32_t)(ukeys[i] & 0xffffffffu);
+}
+
+// ---------------------------------------------------------------- V-cycle kernels (row-major n x k blocks)
+// mode 0: OUT = X + omega * dinv * (B - A X)    (damped Jacobi sweep)      mode 1: OUT = B - A X   (residual)
+template <int G, int KP>
+__global__ void __launch_bounds__(TB) k_smooth(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                               const double* __restrict__ val, const double* __restrict__ dinv,
+                                               const double* __restrict__ B, const double* __restrict__ X,
+                                               double* __restrict__ OUT, int k, int64_t n, double omega, int mode) {
+  constexpr int J = G / KP;
+  constexpr int GROUPS = TB / G;
+  const int lane = threadIdx.x & 31;
+  const int gl = threadIdx.x % G, grp = threadIdx.x / G;
+  const int jsub = gl / KP, r = gl % KP;
+  const bool on = r < k;
+  const int rr = on ? r : 0;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((lane / G) * G));
+  for (int64_t row = (int64_t)blockIdx.x * GROUPS + grp; row < n; row += (int64_t)gridDim.x * GROUPS) {
+    const int64_t s = rowptr[row], e = rowptr[row + 1];
+    double acc = 0.0;
+    for (int64_t base = s; base < e; base += G) {
+      int32_t myc = (int32_t)row;
+      double myv = 0.0;
+      if (base + gl < e) { myc = col[base + gl]; myv = val[base + gl]; }
+#pragma unroll
+      for (int i = 0; i < KP; i++) {
+        const int j = i * J + jsub;
+        const int32_t c = __shfl_sync(gmask, myc, j, G);
+        const double v = __shfl_sync(gmask, myv, j, G);
+        acc = fma(v, X[(int64_t)c * k + rr], acc);
+      }
+    }
+#pragma unroll
+    for (int o = G / 2; o >= KP; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o, G);
+    if (jsub == 0 && on) {
+      const int64_t idx = row * k + r;
+      const double res = B[idx] - acc;
+      OUT[idx] = (mode == 1) ? res : fma(omega * dinv[row], res, X[idx]);
+    }
+  }
+}
+
+__global__ void k_jacobi0(const double* __restrict__ dinv, const double* __restrict__ B, double* __restrict__ X, int k, int64_t n,
+                          double omega) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= n * k) return;
+  X[e] = omega * dinv[e / k] * B[e];
+}
+
+__global__ void k_restrict(const int32_t* __restrict__ members, const double* __restrict__ R, double* __restrict__ BC, int k,
+                           int64_t n, int64_t nc) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= nc * k) return;
+  const int64_t a = e / k;
+  const int r = (int)(e - a * k);
+  double s = 0.0;
+#pragma unroll
+  for (int m = 0; m < AGG; m++) {
+    int64_t i = members ? (int64_t)members[a * AGG + m] : a * AGG + m;
+    if (i >= 0 && i < n) s += R[i * k + r];
+  }
+  BC[e] = s;
+}
+
+__global__ void k_prolong(const int32_t* __restrict__ agg, const double* __restrict__ dinv, const double* __restrict__ XC,
+                          double* __restrict__ X, int k, int64_t n, double alpha) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= n * k) return;
+  const int64_t i = e / k;
+  const int r = (int)(e - i * k);
+  if (dinv[i] == 0.0) return;  // constrained / empty rows stay zero
+  const int64_t a = agg ? (int64_t)agg[i] : i / AGG;
+  X[e] = fma(alpha, XC[a * k + r], X[e]);
+}
+
+// high-order dofs: z = dinv r for rows [n0, n)
+__global__ void k_diag_tail(const double* __restrict__ dinv, const double* __restrict__ R, double* __restrict__ Z, int k, int64_t n0,
+                            int64_t n) {
+  int64_t e = n0 * k + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= n * k) return;
+  Z[e] = dinv[e / k] * R[e];
+}
+
+// ---------------------------------------------------------------- coarsest level: dense inverse
+__global__ void k_dense_fill(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
+                             int n, double* __restrict__ M) {  // M = [A | I], n x 2n
+  for (int e = threadIdx.x; e < n * 2 * n; e += blockDim.x) {
+    const int i = e / (2 * n), j = e - i * 2 * n;
+    M[e] = (j == n + i) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    bool diag = false;
+    for (int64_t j = rowptr[i]; j < rowptr[i + 1]; j++) {
+      M[(int64_t)i * 2 * n + col[j]] = val[j];
+      if (col[j] == i && val[j] > 0.0) diag = true;
+    }
+    if (!diag) M[(int64_t)i * 2 * n + i] = 1.0;  // empty aggregate: identity row keeps the matrix regular
+  }
+}
+
+__global__ void k_dense_invert(int n, double* __restrict__ M) {  // Gauss-Jordan without pivoting (SPD), one CTA
+  extern __shared__ double f[];                                   // column p of the current step
+  const int w = 2 * n;
+  for (int p = 0; p < n; p++) {
+    const double piv = M[(int64_t)p * w + p];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) f[i] = M[(int64_t)i * w + p];
+    __syncthreads();
+    const double ip = 1.0 / piv;
+    for (int j = threadIdx.x; j < w; j += blockDim.x) M[(int64_t)p * w + j] *= ip;
+    __syncthreads();
+    for (int e = threadIdx.x; e < n * w; e += blockDim.x) {
+      const int i = e / w, j = e - i * w;
+      if (i != p) M[e] = fma(-f[i], M[(int64_t)p * w + j], M[e]);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void k_dense_extract(int n, const double* __restrict__ M, double* __restrict__ Ainv) {
+  for (int e = threadIdx.x + blockIdx.x * blockDim.x; e < n * n; e += blockDim.x * gridDim.x) {
+    const int i = e / n, j = e - i * n;
+    Ainv[e] = M[(int64_t)i * 2 * n + n + j];
+  }
+}
+
+__global__ void k_dense_apply(int n, const double* __restrict__ Ainv, const double* __restrict__ B, double* __restrict__ X, int k) {
+  for (int e = threadIdx.x + blockIdx.x * blockDim.x; e < n * k; e += blockDim.x * gridDim.x) {
+    const int i = e / k, r = e - i * k;
+    double s = 0.0;
+    for (int j = 0; j < n; j++) s = fma(Ainv[(int64_t)i * n + j], B[(int64_t)j * k + r], s);
+    X[e] = s;
+  }
+}
+
+int kp_of(int k) {
+  int kp = 1;
+  while (kp < k) kp <<= 1;
+  return kp;
+}
+
+}  // namespace
+
+void spmm_smooth(Ctx* c, const int64_t* rowptr, const int32_t* col, const double* val, const double* dinv, const double* B,
+                 const double* X, double* OUT, int k, int64_t n, double omega, int mode) {
+  const int kp = kp_of(k);
+  const int G = kp <= 8 ? 8 : kp;
+  const int64_t want = (n + (TB / G) - 1) / (TB / G);
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->num_sms * 8));
+  cudaStream_t st = c->stream;
+  switch (kp) {
+    case 1: k_smooth<8, 1><<<grid, TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode); break;
+    case 2: k_smooth<8, 2><<<grid, TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode); break;
+    case 4: k_smooth<8, 4><<<grid, TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode); break;
+    case 8: k_smooth<8, 8><<<grid, TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode); break;
+    case 16: k_smooth<16, 16><<<grid, TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode); break;
+    default: k_smooth<32, 32><<<grid, TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode); break;
+  }
+  c->launches++;
+  CK(cudaGetLastError());
+}
+
+void amg_release(Ctx* c) {
+  cudaStream_t s = c->stream;
+  for (auto& L : c->amg) {
+    L.rowptr.release(s); L.col.release(s); L.val.release(s); L.dinv.release(s); L.agg.release(s); L.members.release(s);
+    L.b.release(s); L.x.release(s); L.t.release(s);
+  }
+  c->amg.clear();
+  c->amg_dense.release(s);
+  c->amg_nrhs = 0;
+}
+
+void amg_setup(Ctx* c) {
+  cudaStream_t st = c->stream;
+  amg_release(c);
+  const int64_t nv = c->nv;
+  c->amg.reserve(MAXLEV);
+  c->amg.emplace_back();
+  {
+    // ---- level 0: free-free part of the leading nv x nv block
+    Ctx::AmgLevel& L = c->amg.back();
+    L.n = nv;
+    DBuf<int32_t> cnt, incl;
+    cnt.ensure(nv, st); incl.ensure(nv, st);
+    LAUNCH(c, k_vv_count, grid_for(nv, TB), TB, 0, c->rowptr.p, c->col.p, c->constrained.p, nv, cnt.p);
+    size_t bytes = 0;
+    CK(cub::DeviceScan::InclusiveSum(nullptr, bytes, cnt.p, incl.p, nv, st));
+    c->tmp.ensure(bytes, st);
+    CK(cub::DeviceScan::InclusiveSum(c->tmp.p, bytes, cnt.p, incl.p, nv, st));
+    c->launches += 2;
+    int32_t total = 0;
+    CK(cudaMemcpyAsync(&total, incl.p + (nv - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    L.nnz = total;
+    L.rowptr.ensure(nv + 1, st); L.col.ensure(total, st); L.val.ensure(total, st); L.dinv.ensure(nv, st);
+    LAUNCH(c, k_excl_to_ptr, grid_for(nv + 1, TB), TB, 0, incl.p, nv, L.rowptr.p);
+    LAUNCH(c, k_vv_fill, grid_for(nv, TB), TB, 0, c->rowptr.p, c->col.p, c->val.p, c->constrained.p, nv, L.rowptr.p, L.col.p, L.val.p);
+    LAUNCH(c, k_level_dinv, grid_for(nv, TB), TB, 0, L.rowptr.p, L.col.p, L.val.p, c->constrained.p, nv, L.dinv.p);
+    cnt.release(st); incl.release(st);
+    // ---- aggregates of level 0 from the Morton ranks of the vertex coordinates
+    DBuf<double> lohi;
+    DBuf<uint64_t> code, codes;
+    DBuf<uint32_t> idx, perm;
+    lohi.ensure(6, st); code.ensure(nv, st); codes.ensure(nv, st); idx.ensure(nv, st); perm.ensure(nv, st);
+    LAUNCH(c, k_bbox, 1, TB, 0, c->xyz.p, nv, c->dim, lohi.p);
+    LAUNCH(c, k_morton, grid_for(nv, TB), TB, 0, c->xyz.p, nv, c->dim, lohi.p, code.p, idx.p);
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, code.p, codes.p, idx.p, perm.p, nv, 0, 63, st));
+    c->tmp.ensure(bytes, st);
+    CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, code.p, codes.p, idx.p, perm.p, nv, 0, 63, st));
+    c->launches += 4;
+    const int64_t nc = (nv + AGG - 1) / AGG;
+    L.agg.ensure(nv, st); L.members.ensure(nc * AGG, st);
+    LAUNCH(c, k_agg_from_perm, grid_for(nc * AGG, TB), TB, 0, perm.p, nv, L.agg.p, L.members.p, nc * AGG);
+    lohi.release(st); code.release(st); codes.release(st); idx.release(st); perm.release(st);
+  }
+  // ---- coarser levels by Galerkin products until the level is small enough for a dense inverse
+  while (c->amg.back().n > COARSEST && (int)c->amg.size() < MAXLEV) {
+    c->amg.emplace_back();
+    Ctx::AmgLevel& F = c->amg[c->amg.size() - 2];
+    Ctx::AmgLevel& C = c->amg.back();
+    const int64_t nc = (F.n + AGG - 1) / AGG;
+    C.n = nc;
+    DBuf<uint64_t> keys, keys2, ukeys;
+    DBuf<double> vals, vals2, uvals;
+    DBuf<int64_t> nruns;
+    keys.ensure(F.nnz, st); keys2.ensure(F.nnz, st); ukeys.ensure(F.nnz, st);
+    vals.ensure(F.nnz, st); vals2.ensure(F.nnz, st); uvals.ensure(F.nnz, st); nruns.ensure(1, st);
+    LAUNCH(c, k_galerkin_pairs, grid_for(F.n, TB), TB, 0, F.rowptr.p, F.col.p, F.val.p, F.agg.p, F.dinv.p, F.n, keys.p, vals.p);
+    size_t bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys.p, keys2.p, vals.p, vals2.p, F.nnz, 0, 64, st));
+    c->tmp.ensure(bytes, st);
+    CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, keys.p, keys2.p, vals.p, vals2.p, F.nnz, 0, 64, st));
+    CK(cub::DeviceReduce::ReduceByKey(nullptr, bytes, keys2.p, ukeys.p, vals2.p, uvals.p, nruns.p, cub::Sum(), F.nnz, st));
+    c->tmp.ensure(bytes, st);
+    CK(cub::DeviceReduce::ReduceByKey(c->tmp.p, bytes, keys2.p, ukeys.p, vals2.p, uvals.p, nruns.p, cub::Sum(), F.nnz, st));
+    c->launches += 8;
+    int64_t hr = 0;
+    uint64_t lastkey = 0;
+    CK(cudaMemcpyAsync(&hr, nruns.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (hr > 0) {
+      CK(cudaMemcpyAsync(&lastkey, ukeys.p + (hr - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (lastkey == ~0ull) hr--;  // the run of dropped (constrained) entries
+    }
+    C.nnz = hr;
+    C.rowptr.ensure(nc + 1, st); C.col.ensure(std::max<int64_t>(hr, 1), st); C.val.ensure(std::max<int64_t>(hr, 1), st); C.dinv.ensure(nc, st);
+    LAUNCH(c, k_coarse_rowptr, grid_for(nc + 1, TB), TB, 0, ukeys.p, hr, nc, C.rowptr.p);
+    if (hr) {
+      LAUNCH(c, k_coarse_cols, grid_for(hr, TB), TB, 0, ukeys.p, hr, C.col.p);
+      CK(cudaMemcpyAsync(C.val.p, uvals.p, hr * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    LAUNCH(c, k_level_dinv, grid_for(nc, TB), TB, 0, C.rowptr.p, C.col.p, C.val.p, (const uint8_t*)nullptr, nc, C.dinv.p);
+    keys.release(st); keys2.release(st); ukeys.release(st); vals.release(st); vals2.release(st); uvals.release(st); nruns.release(st);
+  }
+  // ---- dense inverse of the coarsest level
+  {
+    Ctx::AmgLevel& L = c->amg.back();
+    const int n = (int)L.n;
+    if (n > 2048) FAIL(REMO_ERR_ARG, "amg_setup: coarsest level still has %d rows", n);
+    DBuf<double> M;
+    M.ensure((size_t)n * 2 * n, st);
+    c->amg_dense.ensure((size_t)n * n, st);
+    LAUNCH(c, k_dense_fill, 1, 1024, 0, L.rowptr.p, L.col.p, L.val.p, n, M.p);
+    LAUNCH(c, k_dense_invert, 1, 1024, n * sizeof(double), n, M.p);
+    LAUNCH(c, k_dense_extract, 64, 256, 0, n, M.p, c->amg_dense.p);
+    M.release(st);
+  }
+}
+
+// z_vert = V-cycle(r_vert), z_high = D^-1 r_high.  R, Z: ndof x k blocks of the PCG.
+void amg_apply(Ctx* c, const double* R, double* Z, int k) {
+  cudaStream_t st = c->stream;
+  static const double omega = env_d("REMO_AMG_OMEGA", 0.55);
+  static const double alpha = env_d("REMO_AMG_ALPHA", 1.0);
+  static const int sweeps = (int)env_d("REMO_AMG_SWEEPS", 1);
+  const int nl = (int)c->amg.size();
+  if (c->amg_nrhs != k) {
+    for (auto& L : c->amg) { L.b.ensure(L.n * k, st); L.x.ensure(L.n * k, st); L.t.ensure(L.n * k, st); }
+    c->amg_nrhs = k;
+  }
+  // down
+  for (int l = 0; l < nl - 1; l++) {
+    Ctx::AmgLevel& L = c->amg[l];
+    const double* b = (l == 0) ? R : L.b.p;
+    LAUNCH(c, k_jacobi0, grid_for(L.n * k, TB), TB, 0, L.dinv.p, b, L.x.p, k, L.n, omega);
+    for (int s = 1; s < sweeps; s++) {
+      spmm_smooth(c, L.rowptr.p, L.col.p, L.val.p, L.dinv.p, b, L.x.p, L.t.p, k, L.n, omega, 0);
+      std::swap(L.x.p, L.t.p);
+    }
+    spmm_smooth(c, L.rowptr.p, L.col.p, L.val.p, L.dinv.p, b, L.x.p, L.t.p, k, L.n, omega, 1);  // t = b - A x
+    Ctx::AmgLevel& C = c->amg[l + 1];
+    LAUNCH(c, k_restrict, grid_for(C.n * k, TB), TB, 0, l == 0 ? L.members.p : (const int32_t*)nullptr, L.t.p, C.b.p, k, L.n, C.n);
+  }
+  {  // coarsest: dense inverse
+    Ctx::AmgLevel& L = c->amg[nl - 1];
+    const double* b = (nl == 1) ? R : L.b.p;
+    double* x = (nl == 1) ? Z : L.x.p;
+    LAUNCH(c, k_dense_apply, grid_for(L.n * k, 128), 128, 0, (int)L.n, c->amg_dense.p, b, x, k);
+  }
+  // up
+  for (int l = nl - 2; l >= 0; l--) {
+    Ctx::AmgLevel& L = c->amg[l];
+    Ctx::AmgLevel& C = c->amg[l + 1];
+    const double* b = (l == 0) ? R : L.b.p;
+    LAUNCH(c, k_prolong, grid_for(L.n * k, TB), TB, 0, l == 0 ? L.agg.p : (const int32_t*)nullptr, L.dinv.p, C.x.p, L.x.p, k, L.n, alpha);
+    for (int s = 0; s < sweeps; s++) {
+      double* out = (l == 0 && s == sweeps - 1) ? Z : L.t.p;
+      spmm_smooth(c, L.rowptr.p, L.col.p, L.val.p, L.dinv.p, b, L.x.p, out, k, L.n, omega, 0);
+      if (out == L.t.p) std::swap(L.x.p, L.t.p);
+    }
+  }
+  if (c->ndof > c->nv)
+    LAUNCH(c, k_diag_tail, grid_for((c->ndof - c->nv) * k, TB), TB, 0, c->dinv.p, R, Z, k, c->nv, c->ndof);
+}

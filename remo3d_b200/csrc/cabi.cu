@@ -98,15 +98,25 @@ int remo_ctx_destroy(void* vctx) {
   c->axis_v.release(s); c->axis_z.release(s); c->sv.release(s); c->edge_keys.release(s); c->elem_edges.release(s);
   c->face_keys.release(s); c->elem_faces.release(s); c->constrained.release(s); c->adj_ptr.release(s); c->adj.release(s);
   c->rowptr.release(s); c->col.release(s); c->val.release(s); c->gm.release(s); c->sigma.release(s); c->rvert.release(s);
-  c->dinv.release(s); c->c_rowptr.release(s); c->c_col.release(s); c->c_val.release(s); c->c_dinv.release(s);
-  c->cw0.release(s); c->cw1.release(s); c->cw2.release(s);
+  c->dinv.release(s); amg_release(c);
   c->F.release(s); c->X.release(s); c->R.release(s); c->Z.release(s); c->P.release(s); c->Q.release(s);
   c->partial.release(s); c->scal.release(s); c->iters_d.release(s); c->tmp.release(s);
   cudaStreamSynchronize(s);
   for (int i = 0; i < REMO_NSTAGE; i++) { cudaEventDestroy(c->ev0[i]); cudaEventDestroy(c->ev1[i]); }
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
-  cudaStreamDestroy(s);
+  if (c->own_stream) cudaStreamDestroy(s);
   delete c;
+  return REMO_OK;
+}
+
+int remo_ctx_set_stream(void* vctx, void* stream) {
+  Ctx* c = static_cast<Ctx*>(vctx);
+  if (!c) return REMO_ERR_ARG;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  c->own_stream = false;
+  c->stream = static_cast<cudaStream_t>(stream);
   return REMO_OK;
 }
 

@@ -62,6 +62,7 @@ struct DBuf {
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  bool own_stream = true;
   std::string err;
   int64_t launches = 0;
   int num_sms = 148;
@@ -105,14 +106,19 @@ struct Ctx {
   // ---- preconditioner
   int pkind = -1;
   DBuf<double> dinv;  // ndof: 1/diag on free dofs, 0 on constrained
-  // two-level: vertex-block coarse operator
-  DBuf<int64_t> c_rowptr;
-  DBuf<int32_t> c_col;
-  DBuf<double> c_val;
-  DBuf<double> c_dinv;
-  int64_t c_nnz = 0;
-  int coarse_sweeps = 0;
-  DBuf<double> cw0, cw1, cw2;  // coarse work vectors nv x nrhs
+  // "multigrid": aggregation AMG hierarchy on the vertex (P1) block, see amg.cu
+  struct AmgLevel {
+    int64_t n = 0, nnz = 0;
+    DBuf<int64_t> rowptr;
+    DBuf<int32_t> col;
+    DBuf<double> val, dinv;
+    DBuf<int32_t> agg;        // fine row -> aggregate (coarse row) of the next level
+    DBuf<int32_t> members;    // rows sorted by aggregate (8 per aggregate, -1 padded): deterministic restriction
+    DBuf<double> b, x, t;     // n x nrhs work blocks (level 0 uses R / Z of the PCG directly for b / x)
+  };
+  std::vector<AmgLevel> amg;
+  DBuf<double> amg_dense;     // inverse of the coarsest matrix (n x n)
+  int amg_nrhs = 0;
 
   // ---- right-hand sides / PCG state, row-major ndof x nrhs
   int nrhs = 0;
@@ -174,3 +180,9 @@ void apparent_resistivity(Ctx* c, int npts, const int32_t* pt_rhs, const double*
 void launch_spmm(Ctx* c, const double* P, double* Q, int nrhs);
 void launch_vector_updates(Ctx* c, int nrhs);
 void alloc_solver_state(Ctx* c, int nrhs);
+// amg.cu
+void amg_setup(Ctx* c);
+void amg_apply(Ctx* c, const double* R, double* Z, int nrhs);
+void amg_release(Ctx* c);
+void spmm_smooth(Ctx* c, const int64_t* rowptr, const int32_t* col, const double* val, const double* dinv, const double* B,
+                 const double* X, double* OUT, int k, int64_t n, double omega, int mode);

@@ -12,6 +12,8 @@
 // The columns run in lockstep with their own alpha/beta (device-resident scalars, no host round trip per
 // iteration); a converged column is frozen (alpha = beta = 0).  Dot products are reduced block-wise into a
 // partial array and finished in a fixed order by a one-block kernel -> bit-reproducible runs.
+#include <cstdlib>
+
 #include "space_view.cuh"
 
 namespace {
@@ -67,6 +69,72 @@ __global__ void __launch_bounds__(TB) k_spmm(const int64_t* __restrict__ rowptr,
     for (int w = 0; w < TB / 32; w++) t += sh[w][lane];
     if (lane < KP) partial[(int64_t)blockIdx.x * KMAX + lane] = t;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Variant 3: G-lane group per row.  The plain warp-per-row kernel is LATENCY bound (one dependent
+// rowptr -> col/val -> P chain per warp, 64 rows in flight per SM).  Here a group of G lanes (8 for nrhs <= 8)
+// owns a row, so 32/G rows are in flight per warp; the group loads G consecutive (col,val) pairs with one
+// coalesced request each, broadcasts them by shuffle to its (jsub, r) lanes and issues all G/J gathers of P
+// back to back before the FMAs.  No cross-lane reduction when G == KP.
+// ------------------------------------------------------------------------------------------------
+template <int G, int KP>
+__global__ void __launch_bounds__(TB) k_spmm_g(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                               const double* __restrict__ val, const uint8_t* __restrict__ constrained,
+                                               const double* __restrict__ P, double* __restrict__ Q, int k, int64_t n,
+                                               double* __restrict__ partial) {
+  constexpr int J = G / KP;           // matrix entries processed per step by one group
+  constexpr int GROUPS = TB / G;      // rows in flight per CTA
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = threadIdx.x % G;     // lane within the group
+  const int grp = threadIdx.x / G;
+  const int jsub = gl / KP, r = gl % KP;
+  const bool on = r < k;
+  const int rr = on ? r : 0;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((lane / G) * G));
+  double dot = 0.0;
+  for (int64_t row = (int64_t)blockIdx.x * GROUPS + grp; row < n; row += (int64_t)gridDim.x * GROUPS) {
+    const int64_t s = rowptr[row], e = rowptr[row + 1];
+    double acc = 0.0;
+    // software pipeline: the next chunk's (col,val) are requested before the current chunk's gathers
+    int32_t nc = (int32_t)row;
+    double nv = 0.0;
+    if (s + gl < e) { nc = __ldcs(col + s + gl); nv = __ldcs(val + s + gl); }
+    for (int64_t base = s; base < e; base += G) {
+      const int32_t myc = nc;
+      const double myv = nv;
+      nc = (int32_t)row; nv = 0.0;
+      if (base + G + gl < e) { nc = __ldcs(col + base + G + gl); nv = __ldcs(val + base + G + gl); }
+      double x[KP];
+      double vv[KP];
+#pragma unroll
+      for (int i = 0; i < KP; i++) {
+        const int j = i * J + jsub;
+        const int32_t c = __shfl_sync(gmask, myc, j, G);
+        vv[i] = __shfl_sync(gmask, myv, j, G);
+        x[i] = P[(int64_t)c * k + rr];
+      }
+#pragma unroll
+      for (int i = 0; i < KP; i++) acc = fma(vv[i], x[i], acc);
+    }
+#pragma unroll
+    for (int o = G / 2; o >= KP; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o, G);
+    if (constrained[row]) acc = 0.0;
+    if (jsub == 0 && on) {
+      __stcs(Q + row * k + r, acc);
+      dot = fma(acc, P[row * k + r], dot);
+    }
+  }
+  // per-column block reduction: threads with jsub == 0 hold column r = gl
+  __shared__ double sh[TB];
+  sh[threadIdx.x] = (jsub == 0 && on) ? dot : 0.0;
+  __syncthreads();
+  if (threadIdx.x < KP) {
+    double t = 0.0;
+    for (int i = threadIdx.x; i < TB; i += G) t += sh[i];
+    partial[(int64_t)blockIdx.x * KMAX + threadIdx.x] = t;
+  }
+  (void)warp;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -354,14 +422,41 @@ void alloc_solver_state(Ctx* c, int nrhs) {
   c->F.ensure(n, st); c->X.ensure(n, st); c->R.ensure(n, st);
   c->Z.ensure(n, st); c->P.ensure(n, st); c->Q.ensure(n, st);
   c->partial.ensure((size_t)std::max(vec_grid(c), spmm_grid(c)) * 2 * KMAX, st);
+  CK(cudaMemsetAsync(c->partial.p, 0, c->partial.n * sizeof(double), st));
   c->scal.ensure(S_NSLOT * KMAX, st);
   c->iters_d.ensure(KMAX, st);
   c->nrhs = nrhs;
 }
 
+static int spmm_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("REMO_SPMM_VARIANT");
+    v = e ? atoi(e) : 3;
+  }
+  return v;
+}
+
 void launch_spmm(Ctx* c, const double* P, double* Q, int nrhs) {
   const int kp = kp_for(nrhs);
   const int grid = spmm_grid(c);
+  if (spmm_variant() == 3) {
+    auto* rp = c->rowptr.p; auto* cl = c->col.p; auto* vl = c->val.p; auto* cs = c->constrained.p;
+    double* pt = c->partial.p;
+    const int64_t n = c->ndof;
+    cudaStream_t st = c->stream;
+    switch (kp) {
+      case 1: k_spmm_g<8, 1><<<grid, TB, 0, st>>>(rp, cl, vl, cs, P, Q, nrhs, n, pt); break;
+      case 2: k_spmm_g<8, 2><<<grid, TB, 0, st>>>(rp, cl, vl, cs, P, Q, nrhs, n, pt); break;
+      case 4: k_spmm_g<8, 4><<<grid, TB, 0, st>>>(rp, cl, vl, cs, P, Q, nrhs, n, pt); break;
+      case 8: k_spmm_g<8, 8><<<grid, TB, 0, st>>>(rp, cl, vl, cs, P, Q, nrhs, n, pt); break;
+      case 16: k_spmm_g<16, 16><<<grid, TB, 0, st>>>(rp, cl, vl, cs, P, Q, nrhs, n, pt); break;
+      default: k_spmm_g<32, 32><<<grid, TB, 0, st>>>(rp, cl, vl, cs, P, Q, nrhs, n, pt); break;
+    }
+    c->launches++;
+    CK(cudaGetLastError());
+    return;
+  }
   DISPATCH_KP(kp, (k_spmm<KP><<<grid, TB, 0, c->stream>>>(c->rowptr.p, c->col.p, c->val.p, c->constrained.p, P, Q, nrhs, c->ndof, c->partial.p)));
   c->launches++;
   CK(cudaGetLastError());
@@ -382,7 +477,7 @@ void precond_setup(Ctx* c, int kind) {
   StageTimer timer(c, ST_PRECOND);
   c->dinv.ensure(c->ndof, c->stream);
   LAUNCH(c, k_dinv, grid_for(c->ndof, TB), TB, 0, c->rowptr.p, c->col.p, c->val.p, c->constrained.p, c->dinv.p, c->ndof);
-  if (kind == REMO_PRECOND_MULTIGRID) FAIL(REMO_ERR_ARG, "remo_precond_setup: two-level preconditioner not built yet");
+  if (kind == REMO_PRECOND_MULTIGRID) amg_setup(c);
   c->pkind = kind;
 }
 
@@ -424,11 +519,18 @@ int solve(Ctx* c, double rtol, int maxit, int* iters, double* relres) {
   const int k = c->nrhs, kp = kp_for(k);
   const int64_t n = c->ndof;
   const int vg = vec_grid(c), sg = spmm_grid(c);
-  const int jac = 1;
+  const int jac = (c->pkind == REMO_PRECOND_LOCAL) ? 1 : 0;
 
   DISPATCH_KP(kp, (k_init<KP><<<vg, TB, 0, st>>>(c->F.p, c->constrained.p, c->dinv.p, c->X.p, c->R.p, c->Z.p, c->P.p, k, n, jac, c->partial.p)));
+  c->launches++;
+  if (!jac) {
+    amg_apply(c, c->R.p, c->Z.p, k);
+    DISPATCH_KP(kp, (k_dot_rz<KP><<<vg, TB, 0, st>>>(c->R.p, c->Z.p, k, n, c->partial.p)));
+    CK(cudaMemcpyAsync(c->P.p, c->Z.p, (size_t)n * k * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    c->launches++;
+  }
   k_scal_init<<<1, 1024, 0, st>>>(c->partial.p, vg, c->scal.p, c->iters_d.p, k, rtol);
-  c->launches += 2;
+  c->launches++;
   CK(cudaGetLastError());
 
   const int check_every = 16;
@@ -451,6 +553,11 @@ int solve(Ctx* c, double rtol, int maxit, int* iters, double* relres) {
       if (c->prof) CK(cudaEventRecord(c->prof_ev[pe + 1], st));
       k_scal_alpha<<<1, 1024, 0, st>>>(c->partial.p, sg, c->scal.p);
       DISPATCH_KP(kp, (k_update_xr<KP><<<vg, TB, 0, st>>>(c->X.p, c->R.p, c->P.p, c->Q.p, c->dinv.p, c->Z.p, c->scal.p, k, n, jac, c->partial.p)));
+      if (!jac) {
+        amg_apply(c, c->R.p, c->Z.p, k);
+        DISPATCH_KP(kp, (k_dot_rz<KP><<<vg, TB, 0, st>>>(c->R.p, c->Z.p, k, n, c->partial.p)));
+        c->launches++;
+      }
       k_scal_beta<<<1, 1024, 0, st>>>(c->partial.p, vg, c->scal.p, c->iters_d.p);
       DISPATCH_KP(kp, (k_update_p<KP><<<vg, TB, 0, st>>>(c->P.p, c->Z.p, c->scal.p, k, n)));
       c->launches += 4;

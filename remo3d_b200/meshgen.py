@@ -269,17 +269,19 @@ def half_ball_mesh(radius, electrodes_z, material=None, **kw):
 
     half = kw.get("half", True)
     pts, n_axis, _ = half_ball_points(radius, electrodes_z, **kw)
-    # Morton order (locality of vertex numbers -> locality of CSR columns)
-    q = np.clip(((pts + radius) / (2 * radius) * 1023).astype(np.int64), 0, 1023)
+    # Morton order with 21 bits per axis (locality of vertex numbers -> locality of CSR columns, at every
+    # refinement level: the finest cells here are ~1e-4 of the domain)
+    q = np.clip(((pts + radius) / (2 * radius) * (2 ** 21 - 1)).astype(np.uint64), 0, 2 ** 21 - 1)
 
     def spread(v):
-        v = (v | (v << 16)) & 0x030000FF
-        v = (v | (v << 8)) & 0x0300F00F
-        v = (v | (v << 4)) & 0x030C30C3
-        v = (v | (v << 2)) & 0x09249249
+        v = (v | (v << np.uint64(32))) & np.uint64(0x1F00000000FFFF)
+        v = (v | (v << np.uint64(16))) & np.uint64(0x1F0000FF0000FF)
+        v = (v | (v << np.uint64(8))) & np.uint64(0x100F00F00F00F00F)
+        v = (v | (v << np.uint64(4))) & np.uint64(0x10C30C30C30C30C3)
+        v = (v | (v << np.uint64(2))) & np.uint64(0x1249249249249249)
         return v
 
-    code = spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+    code = spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1)) | (spread(q[:, 2]) << np.uint64(2))
     pts = pts[np.argsort(code, kind="stable")]
     # Qhull is ~10x slower with thousands of exactly coplanar hull points (the symmetry plane):
     # triangulate a copy whose plane points are lifted by <= 2e-11 R, keep the exact coordinates;

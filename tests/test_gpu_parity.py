@@ -101,6 +101,29 @@ def test_solve_matches_oracle(ctx, order):
     np.testing.assert_allclose(ra, ref["ra"], rtol=1e-6)
 
 
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_multigrid_preconditioner_same_solution(ctx, order):
+    """'multigrid' (hierarchical two-level + aggregation AMG on the P1 block) must reach the same solution as the
+    oracle, in far fewer iterations than 'local' (Jacobi)."""
+    mesh, sigma, flat, _ = helpers.ball_case()
+    ref = fo.solve_task(mesh.points, mesh.elems, mesh.mat, sigma, mesh.bfacets, mesh.dirichlet_flags("dirichlet_boundary"), order, flat)
+    _setup(ctx, mesh, order)
+    ctx.assemble(sigma)
+    ctx.rhs_point_sources(flat["src_ptr"], flat["src_z"], flat["src_fac"])
+    ctx.precond_setup("local")
+    it_jac, _ = ctx.solve(rtol=1e-10, maxit=20000)
+    ctx.precond_setup("multigrid")
+    it_mg, relres = ctx.solve(rtol=1e-10, maxit=2000)
+    assert (relres <= 1e-10).all()
+    assert it_mg.max() * 1.4 < it_jac.max(), (it_mg, it_jac)
+    ra = ctx.apparent_resistivity(flat["pt_rhs"], flat["pt_z0"], flat["pt_z1"], flat["pt_k"], flat["scale"])
+    np.testing.assert_allclose(ra, ref["ra"], rtol=1e-6)
+    for r in range(ctx.nrhs):
+        u = ctx.solution(r)
+        assert np.linalg.norm(u - ref["U"][:, r]) <= 1e-6 * np.linalg.norm(ref["U"][:, r])
+    print("order", order, "iterations jacobi", it_jac.tolist(), "multigrid", it_mg.tolist())
+
+
 def test_homogeneous_ball_gives_rho(ctx):
     """Known answer: homogeneous medium -> Ra == rho for every tool, up to discretisation error."""
     mesh, sigma, flat, _ = helpers.ball_case(h_electrode=0.03, h_axis=0.12, grading=0.4, layered=False)
