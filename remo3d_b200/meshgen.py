@@ -346,6 +346,8 @@ def layered_material(layer_tops, dip_rad=0.0, borehole_radius=0.1, invasion=None
 
     def fn(c):
         rho = np.hypot(c[:, 0], c[:, 1])
+        # borehole radius: constant, or a caliper profile (z, r) interpolated along the axis
+        rb = borehole_radius if np.isscalar(borehole_radius) else np.interp(c[:, 2], borehole_radius[0], borehole_radius[1])
         zeff = c[:, 2] - np.tan(dip_rad) * c[:, 0]
         layer = np.searchsorted(tops, zeff)
         m = np.empty(c.shape[0], np.int32)
@@ -358,7 +360,7 @@ def layered_material(layer_tops, dip_rad=0.0, borehole_radius=0.1, invasion=None
         if inclusion is not None:
             cen, rad = inclusion
             m[np.linalg.norm(c - np.asarray(cen), axis=1) < rad] = nxt
-        m[rho < borehole_radius] = 0
+        m[rho < rb] = 0
         return m
 
     fn.n_materials = n_materials
