@@ -251,8 +251,11 @@ def run_b200(args):
 # CPU arm: the oracle (NumPy/SciPy restatement of the reference path) farmed over the host cores
 # ------------------------------------------------------------------------------------------------
 def _cpu_task(payload):
+    from threadpoolctl import threadpool_limits
+
     from oracle import fem_oracle as fo
 
+    threadpool_limits(1)  # one BLAS/OpenMP thread per worker process: the farm supplies the parallelism
     m, flat, order = payload
     t0 = time.time()
     res = fo.solve_task(m["points"], m["elems"], m["mat"], SIGMA, m["bfacets"], m["bdir"].astype(bool), order, flat, solver="pcg")

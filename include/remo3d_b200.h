@@ -115,6 +115,10 @@ int remo_solution_get(void* ctx, int rhs, double* u);
  *   which = 1: numeric assembly (remo_assemble's kernels)
  *   which = 2: PCG vector update kernels for nrhs columns                                       */
 int remo_kernel_time(void* ctx, int which, int nrhs, int reps, float* ms);
+/* Solver tunables (defaults in parentheses): "amg_sweeps" (1) pre = post damped-Jacobi sweeps per AMG level,
+ * "amg_alpha" (1.5) scaling of the coarse-grid correction, "amg_omega_scale" (1.0) weight of the l1-Jacobi sweeps,
+ * must be <= 1 (changing it invalidates the preconditioner: call remo_precond_setup again).                        */
+int remo_set_option(void* ctx, const char* name, double value);
 /* Per-launch timing of the SpMM inside remo_solve: while on, CUDA events bracket every SpMM launch of the
  * PCG loop on the context's stream; remo_profile_get returns the summed milliseconds and the launch count
  * since remo_profile(ctx, 1).  (bench.py roofline: average launch duration inside the timed region.)    */

@@ -37,6 +37,7 @@ SIGNATURES = {
     "remo_apparent_resistivity": (C.c_int, [_p, C.c_int, _p, _p, _p, _p, C.c_double, _p]),
     "remo_solution_get": (C.c_int, [_p, C.c_int, _p]),
     "remo_kernel_time": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "remo_set_option": (C.c_int, [_p, C.c_char_p, C.c_double]),
     "remo_profile": (C.c_int, [_p, C.c_int]),
     "remo_profile_get": (C.c_int, [_p, C.POINTER(C.c_double), _i64p]),
     "remo_launch_count": (C.c_int64, [_p]),
@@ -204,6 +205,9 @@ class Context:
         ms = C.c_float()
         self._ck(self.lib.remo_kernel_time(self.h, int(which), int(nrhs), int(reps), C.byref(ms)))
         return ms.value
+
+    def set_option(self, name, value):
+        self._ck(self.lib.remo_set_option(self.h, name.encode(), float(value)))
 
     def profile(self, on=True):
         self._ck(self.lib.remo_profile(self.h, 1 if on else 0))

@@ -12,12 +12,13 @@
 //   * the V-cycle hierarchy is built on the GPU by plain aggregation: vertices are ranked along a Morton curve of
 //     their coordinates and every 8 consecutive ranks form an aggregate (coarse levels: 8 consecutive rows), the
 //     coarse operators are Galerkin products with piecewise-constant prolongation (sort + reduce-by-key), the
-//     coarsest level (<= 256 rows) is inverted densely.  Smoother: damped Jacobi, symmetric cycle -> M is SPD and
-//     plain PCG applies.
+//     coarsest level (<= 256 rows) is inverted densely.  Smoother: l1-Jacobi (always a contraction), symmetric cycle,
+//     coarse correction over-weighted by 1.5 (plain aggregation under-corrects) -> M is SPD and plain PCG applies.
 // Everything works on row-major n x nrhs blocks, like the PCG.
 #include <cub/cub.cuh>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "space_view.cuh"
 
@@ -68,15 +69,21 @@ __global__ void k_excl_to_ptr(const int32_t* __restrict__ incl, int64_t n, int64
   ptr[i] = (i == 0) ? 0 : (int64_t)incl[i - 1];
 }
 
+// smoother diagonal: l1-Jacobi, dinv_i = 1 / sum_j |a_ij|.  D_l1 - A is diagonally dominant with a non-negative
+// diagonal, hence positive semi-definite: the sweep x += dinv (b - A x) is a contraction in the A-norm for any SPD A
+// (no global eigenvalue estimate needed, robust on sliver elements), and the symmetric V-cycle is SPD.
+// dinv = 0 marks rows outside the coarse space (constrained vertices, empty aggregates).
 __global__ void k_level_dinv(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
                              const uint8_t* __restrict__ con, int64_t n, double* __restrict__ dinv) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double d = 0.0;
+  double d = 0.0, l1 = 0.0;
   if (!(con && con[i]))
-    for (int64_t j = rowptr[i]; j < rowptr[i + 1]; j++)
+    for (int64_t j = rowptr[i]; j < rowptr[i + 1]; j++) {
+      l1 += fabs(val[j]);
       if (col[j] == (int32_t)i) d = val[j];
-  dinv[i] = d > 0.0 ? 1.0 / d : 0.0;
+    }
+  dinv[i] = d > 0.0 ? 1.0 / l1 : 0.0;
 }
 
 // ---------------------------------------------------------------- Morton ranks of the vertices
@@ -423,6 +430,7 @@ void amg_setup(Ctx* c) {
     LAUNCH(c, k_level_dinv, grid_for(nc, TB), TB, 0, C.rowptr.p, C.col.p, C.val.p, (const uint8_t*)nullptr, nc, C.dinv.p);
     keys.release(st); keys2.release(st); ukeys.release(st); vals.release(st); vals2.release(st); uvals.release(st); nruns.release(st);
   }
+  for (auto& L : c->amg) L.omega = c->amg_omega_scale;  // l1-Jacobi: any weight <= 1 keeps the cycle SPD
   // ---- dense inverse of the coarsest level
   {
     Ctx::AmgLevel& L = c->amg.back();
@@ -441,9 +449,8 @@ void amg_setup(Ctx* c) {
 // z_vert = V-cycle(r_vert), z_high = D^-1 r_high.  R, Z: ndof x k blocks of the PCG.
 void amg_apply(Ctx* c, const double* R, double* Z, int k) {
   cudaStream_t st = c->stream;
-  static const double omega = env_d("REMO_AMG_OMEGA", 0.55);
-  static const double alpha = env_d("REMO_AMG_ALPHA", 1.0);
-  static const int sweeps = (int)env_d("REMO_AMG_SWEEPS", 1);
+  const double alpha = c->amg_alpha;
+  const int sweeps = c->amg_sweeps;
   const int nl = (int)c->amg.size();
   if (c->amg_nrhs != k) {
     for (auto& L : c->amg) { L.b.ensure(L.n * k, st); L.x.ensure(L.n * k, st); L.t.ensure(L.n * k, st); }
@@ -453,6 +460,7 @@ void amg_apply(Ctx* c, const double* R, double* Z, int k) {
   for (int l = 0; l < nl - 1; l++) {
     Ctx::AmgLevel& L = c->amg[l];
     const double* b = (l == 0) ? R : L.b.p;
+    const double omega = L.omega;
     LAUNCH(c, k_jacobi0, grid_for(L.n * k, TB), TB, 0, L.dinv.p, b, L.x.p, k, L.n, omega);
     for (int s = 1; s < sweeps; s++) {
       spmm_smooth(c, L.rowptr.p, L.col.p, L.val.p, L.dinv.p, b, L.x.p, L.t.p, k, L.n, omega, 0);
@@ -473,6 +481,7 @@ void amg_apply(Ctx* c, const double* R, double* Z, int k) {
     Ctx::AmgLevel& L = c->amg[l];
     Ctx::AmgLevel& C = c->amg[l + 1];
     const double* b = (l == 0) ? R : L.b.p;
+    const double omega = L.omega;
     LAUNCH(c, k_prolong, grid_for(L.n * k, TB), TB, 0, l == 0 ? L.agg.p : (const int32_t*)nullptr, L.dinv.p, C.x.p, L.x.p, k, L.n, alpha);
     for (int s = 0; s < sweeps; s++) {
       double* out = (l == 0 && s == sweeps - 1) ? Z : L.t.p;

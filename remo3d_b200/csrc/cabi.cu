@@ -317,6 +317,18 @@ int remo_kernel_time(void* vctx, int which, int nrhs, int reps, float* ms) {
   });
 }
 
+int remo_set_option(void* vctx, const char* name, double value) {
+  return guarded(vctx, [&](Ctx* c) {
+    if (!name) FAIL(REMO_ERR_ARG, "remo_set_option: NULL name");
+    const std::string n(name);
+    if (n == "amg_alpha") c->amg_alpha = value;
+    else if (n == "amg_sweeps") c->amg_sweeps = std::max(1, (int)value);
+    else if (n == "amg_omega_scale") { c->amg_omega_scale = value; c->pkind = -1; }
+    else FAIL(REMO_ERR_ARG, "remo_set_option: unknown option '%s'", name);
+    return REMO_OK;
+  });
+}
+
 int remo_profile(void* vctx, int on) {
   Ctx* c = static_cast<Ctx*>(vctx);
   if (!c) return REMO_ERR_ARG;

@@ -114,9 +114,13 @@ struct Ctx {
     DBuf<double> val, dinv;
     DBuf<int32_t> agg;        // fine row -> aggregate (coarse row) of the next level
     DBuf<int32_t> members;    // rows sorted by aggregate (8 per aggregate, -1 padded): deterministic restriction
+    double omega = 1.0;       // weight of the l1-Jacobi sweeps
     DBuf<double> b, x, t;     // n x nrhs work blocks (level 0 uses R / Z of the PCG directly for b / x)
   };
   std::vector<AmgLevel> amg;
+  double amg_alpha = 1.5, amg_omega_scale = 1.0;  // coarse-correction scaling, weight of the l1-Jacobi sweeps (<= 1)
+  int amg_sweeps = 1;                              // pre = post smoothing sweeps
+  int amg_gamma = 1;                               // cycle index: 1 = V, 2 = W
   DBuf<double> amg_dense;     // inverse of the coarsest matrix (n x n)
   int amg_nrhs = 0;
 

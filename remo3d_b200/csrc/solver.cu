@@ -579,7 +579,8 @@ int solve(Ctx* c, double rtol, int maxit, int* iters, double* relres) {
     const double rel = bb > 0.0 ? sqrt(rr / bb) : 0.0;
     if (iters) iters[r] = hit[r];
     if (relres) relres[r] = rel;
-    if (hs[S_ACTIVE * KMAX + r] != 0.0) conv = false;
+    // converged means the residual criterion is met -- a column frozen by a breakdown (r.z <= 0) is NOT converged
+    if (bb > 0.0 && !(rr <= hs[S_TOL2 * KMAX + r])) conv = false;
   }
   if (c->prof) {
     for (int q = 0; q < it; q++) {

