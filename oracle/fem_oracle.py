@@ -186,9 +186,13 @@ class Space:
         ekeys = np.stack([se[:, [i, j]] for (i, j) in le], axis=1).reshape(-1, 2)
         self.edges, inv = _unique_rows(ekeys)
         self.elem_edges = inv.reshape(nt, len(le))
-        fkeys = np.stack([se[:, [i, j, k]] for (i, j, k) in lf], axis=1).reshape(-1, 3)
-        self.faces, inv = _unique_rows(fkeys)
-        self.elem_faces = inv.reshape(nt, len(lf))
+        if dim == 3:
+            fkeys = np.stack([se[:, [i, j, k]] for (i, j, k) in lf], axis=1).reshape(-1, 3)
+            self.faces, inv = _unique_rows(fkeys)
+            self.elem_faces = inv.reshape(nt, len(lf))
+        else:  # 2D: the order-3 "face" function is the cell bubble, numbered by element
+            self.faces = se.copy()
+            self.elem_faces = np.arange(nt).reshape(nt, 1)
         self.ne, self.nf, self.nt = self.edges.shape[0], self.faces.shape[0], nt
         p = order
         self.edge_base = self.nv

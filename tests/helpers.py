@@ -40,3 +40,20 @@ def ball_case(h_electrode=0.08, h_axis=0.3, grading=0.5, tools=("A2.0M0.5N", "N0
     mesh = Mesh(m["points"], m["elems"], m["mat"], m["bfacets"], m["bc"], m["bc_names"])
     flat = planner.flatten_task(task, params, three_d=True)
     return mesh, sigma, flat, params
+
+
+def disc_case(h_electrode=0.03, h_axis=0.15, h_borehole=0.25, grading=0.6, tools=("A2.0M0.5N", "N0.5M2.0A", "B5.7A0.4M"),
+              depths=(10.0, 10.1, 10.2), radius=50.0):
+    """2D axisymmetric half-disc around the first task of a small plan: borehole with a caliper, three beds, one invaded."""
+    from remo3d_b200 import meshgen2d
+
+    params, sec = tl.set_tools_parameters(list(tools), True)
+    _, tasks = planner.prepare_simulation_depths_and_tasks(params, sec, np.asarray(depths, dtype=float), 5)
+    task = tasks[0]
+    wall = (np.array([-60.0, -3.0, 0.0, 2.0, 60.0]), np.array([0.1, 0.11, 0.1, 0.12, 0.1]))
+    m = meshgen2d.half_disc_mesh(radius, task[1][0], wall, [-1.0, 1.5], [None, 0.4, None], h_electrode=h_electrode, h_axis=h_axis,
+                                 h_borehole=h_borehole, grading=grading)
+    mesh = Mesh(m["points"], m["elems"], m["mat"], m["bfacets"], m["bc"], m["bc_names"])
+    sigma = [1 / 1.0, 1 / 10.0, 1 / 5.0, 1 / 100.0, 1 / 10.0]
+    flat = planner.flatten_task(task, params, three_d=False)
+    return mesh, sigma, flat, params

@@ -1,9 +1,10 @@
 """End-to-end pin against the reference's own committed output: `Model.compute_synthetic_logs` on the inputs of
 Examples/Example_01 vs `Examples/Example_01/Output/Results_2024_08_17__18_59_29/Results_1.txt` (tests/golden/example_01).
 
-The reference solved a 2D axisymmetric Netgen mesh at order 3; here the same model is solved on this repo's 3D half-ball
-mesh (materials per tet centroid, interfaces not conforming), so agreement is expected at the discretisation level
-(a few per cent), not at the reference's 3e-4 mesh-noise level.  Depths are chosen inside thick beds."""
+The reference solved 2D axisymmetric Netgen meshes at order 3.  Two runs:
+  * the same 2D axisymmetric path here (conforming 2D mesher, order 3): agreement at the reference's mesh-noise level;
+  * the 3D half-ball path with a tiny dip (materials per tet centroid, interfaces not conforming, order 2): agreement
+    at the discretisation level (a couple of per cent).  Depths are chosen inside thick beds."""
 import os
 
 import numpy as np
@@ -12,6 +13,27 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 TOL = 0.04
+
+
+def test_example01_2d_path_matches_reference_output(golden_dir):
+    from remo3d_b200 import Model
+
+    d = os.path.join(golden_dir, "example_01")
+    gold = np.loadtxt(os.path.join(d, "Results_1.txt"), skiprows=2)
+    names = open(os.path.join(d, "Results_1.txt")).readline().split()[1:]
+    tools = ["A2.0M0.5N", "N0.5M2.0A", "M1.0A0.1B", "B5.7A0.4M"]
+    depths = np.arange(4.0, 8.01, 0.5)  # crosses the 3.05-8.35 m invaded bed
+    model = Model.compute_synthetic_logs(tools, depths, os.path.join(d, "Formation.txt"), os.path.join(d, "Borehole.txt"),
+                                         cpu_workers=4, gpu_workers=1)  # defaults: dip 0 -> 2D, order 3, multigrid
+    worst = 0.0
+    for t in tools:
+        col = names.index(t) + 1
+        ref = np.array([gold[np.argmin(np.abs(gold[:, 0] - z)), col] for z in depths])
+        rel = np.abs(model.logs[t][:, 1] - ref) / ref
+        print(t, "rel", np.round(rel, 5))
+        worst = max(worst, rel.max())
+    assert all(r is not None and "error" not in r for r in model.task_records), model.task_records
+    assert worst < 5e-3, worst
 
 
 def test_example01_logs_match_reference_output(golden_dir):
@@ -23,7 +45,7 @@ def test_example01_logs_match_reference_output(golden_dir):
     tools = ["A2.0M0.5N", "N0.5M2.0A", "M1.0A0.1B"]
     depths = np.array([5.5, 6.0, 15.0, 15.5])
     model = Model.compute_synthetic_logs(tools, depths, os.path.join(d, "Formation.txt"), os.path.join(d, "Borehole.txt"),
-                                         borehole_units=["M", "MM"], cpu_workers=4, gpu_workers=1, order=2,
+                                         dip=0.01, cpu_workers=4, gpu_workers=1, order=2,
                                          mesh_options={"h_electrode": 0.012, "h_axis": 0.035, "grading": 0.28})
     worst = 0.0
     for t in tools:

@@ -177,3 +177,36 @@ def test_error_paths(ctx):
     with pytest.raises(_cabi.RemoError) as e:
         ctx.solve(rtol=1e-14, maxit=2)
     assert e.value.code == _cabi.ERR_NOCONV
+
+
+# ---------------------------------------------------------------------------------------------- 2D axisymmetric path
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_2d_axisymmetric_matches_oracle(ctx, order):
+    """ngsolve_functions.py:34: 2 pi r sigma grad u . grad v on triangles (cell bubble at order 3), Dirichlet = bc [2]."""
+    mesh, sigma, flat, _ = helpers.disc_case()
+    flags = mesh.dirichlet_flags([2])
+    ctx.mesh_set(2, mesh.points, mesh.elems, mesh.mat, mesh.bfacets, flags, mesh.axis_vertices())
+    ctx.space_build(order)
+    space = fo.Space(mesh.nv, mesh.elems, order, 2)
+    assert ctx.ndof == space.ndof and ctx.ne == space.ne
+    edges, _, ee, _ = ctx.topology()
+    np.testing.assert_array_equal(edges, space.edges)
+    np.testing.assert_array_equal(ee, space.elem_edges)
+    np.testing.assert_array_equal(ctx.dirichlet(), space.dirichlet_dofs(mesh.bfacets, flags))
+    ctx.assemble(sigma)
+    rowptr, col, val = ctx.matrix()
+    A = fo.assemble(mesh.points, space, sigma, mesh.mat)
+    np.testing.assert_array_equal(rowptr, A.indptr)
+    np.testing.assert_array_equal(col, A.indices)
+    assert np.linalg.norm(val - A.data) <= 1e-12 * np.linalg.norm(A.data)
+    ref = fo.solve_task(mesh.points, mesh.elems, mesh.mat, sigma, mesh.bfacets, flags, order, flat, dim=2, solver="direct")
+    for pre in ("local", "multigrid"):
+        ctx.precond_setup(pre)
+        ctx.rhs_point_sources(flat["src_ptr"], flat["src_z"], flat["src_fac"])
+        iters, relres = ctx.solve(rtol=1e-10, maxit=20000)
+        assert (relres <= 1e-10).all()
+        ra = ctx.apparent_resistivity(flat["pt_rhs"], flat["pt_z0"], flat["pt_z1"], flat["pt_k"], flat["scale"])
+        np.testing.assert_allclose(ra, ref["ra"], rtol=1e-6)
+        for r in range(ctx.nrhs):
+            u = ctx.solution(r)
+            assert np.linalg.norm(u - ref["U"][:, r]) <= 1e-6 * np.linalg.norm(ref["U"][:, r])
