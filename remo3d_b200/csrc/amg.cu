@@ -345,104 +345,107 @@ void amg_release(Ctx* c) {
   c->amg.clear();
   c->amg_dense.release(s);
   c->amg_nrhs = 0;
+  c->amg_nlev = 0;
 }
 
+// The level objects (and all temporaries, scratch slots of the context) persist across meshes: setup only grows buffers.
 void amg_setup(Ctx* c) {
   cudaStream_t st = c->stream;
-  amg_release(c);
   const int64_t nv = c->nv;
-  c->amg.reserve(MAXLEV);
-  c->amg.emplace_back();
+  if (c->amg.capacity() < MAXLEV) c->amg.reserve(MAXLEV);
+  if (c->amg.empty()) c->amg.emplace_back();
+  int nlev = 1;
+  size_t bytes = 0;
   {
     // ---- level 0: free-free part of the leading nv x nv block
-    Ctx::AmgLevel& L = c->amg.back();
+    Ctx::AmgLevel& L = c->amg[0];
     L.n = nv;
-    DBuf<int32_t> cnt, incl;
-    cnt.ensure(nv, st); incl.ensure(nv, st);
-    LAUNCH(c, k_vv_count, grid_for(nv, TB), TB, 0, c->rowptr.p, c->col.p, c->constrained.p, nv, cnt.p);
-    size_t bytes = 0;
-    CK(cub::DeviceScan::InclusiveSum(nullptr, bytes, cnt.p, incl.p, nv, st));
+    int32_t* cnt = scratch<int32_t>(c, 4, nv);
+    int32_t* incl = scratch<int32_t>(c, 5, nv);
+    LAUNCH(c, k_vv_count, grid_for(nv, TB), TB, 0, c->rowptr.p, c->col.p, c->constrained.p, nv, cnt);
+    CK(cub::DeviceScan::InclusiveSum(nullptr, bytes, cnt, incl, nv, st));
     c->tmp.ensure(bytes, st);
-    CK(cub::DeviceScan::InclusiveSum(c->tmp.p, bytes, cnt.p, incl.p, nv, st));
+    CK(cub::DeviceScan::InclusiveSum(c->tmp.p, bytes, cnt, incl, nv, st));
     c->launches += 2;
     int32_t total = 0;
-    CK(cudaMemcpyAsync(&total, incl.p + (nv - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&total, incl + (nv - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     L.nnz = total;
     L.rowptr.ensure(nv + 1, st); L.col.ensure(total, st); L.val.ensure(total, st); L.dinv.ensure(nv, st);
-    LAUNCH(c, k_excl_to_ptr, grid_for(nv + 1, TB), TB, 0, incl.p, nv, L.rowptr.p);
+    LAUNCH(c, k_excl_to_ptr, grid_for(nv + 1, TB), TB, 0, incl, nv, L.rowptr.p);
     LAUNCH(c, k_vv_fill, grid_for(nv, TB), TB, 0, c->rowptr.p, c->col.p, c->val.p, c->constrained.p, nv, L.rowptr.p, L.col.p, L.val.p);
     LAUNCH(c, k_level_dinv, grid_for(nv, TB), TB, 0, L.rowptr.p, L.col.p, L.val.p, c->constrained.p, nv, L.dinv.p);
-    cnt.release(st); incl.release(st);
     // ---- aggregates of level 0 from the Morton ranks of the vertex coordinates
-    DBuf<double> lohi;
-    DBuf<uint64_t> code, codes;
-    DBuf<uint32_t> idx, perm;
-    lohi.ensure(6, st); code.ensure(nv, st); codes.ensure(nv, st); idx.ensure(nv, st); perm.ensure(nv, st);
-    LAUNCH(c, k_bbox, 1, TB, 0, c->xyz.p, nv, c->dim, lohi.p);
-    LAUNCH(c, k_morton, grid_for(nv, TB), TB, 0, c->xyz.p, nv, c->dim, lohi.p, code.p, idx.p);
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, code.p, codes.p, idx.p, perm.p, nv, 0, 63, st));
+    double* lohi = scratch<double>(c, 9, 8);
+    uint64_t* code = scratch<uint64_t>(c, 0, nv);
+    uint64_t* codes = scratch<uint64_t>(c, 1, nv);
+    uint32_t* idx = scratch<uint32_t>(c, 2, nv);
+    uint32_t* perm = scratch<uint32_t>(c, 3, nv);
+    LAUNCH(c, k_bbox, 1, TB, 0, c->xyz.p, nv, c->dim, lohi);
+    LAUNCH(c, k_morton, grid_for(nv, TB), TB, 0, c->xyz.p, nv, c->dim, lohi, code, idx);
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, code, codes, idx, perm, nv, 0, 63, st));
     c->tmp.ensure(bytes, st);
-    CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, code.p, codes.p, idx.p, perm.p, nv, 0, 63, st));
+    CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, code, codes, idx, perm, nv, 0, 63, st));
     c->launches += 4;
     const int64_t nc = (nv + AGG - 1) / AGG;
     L.agg.ensure(nv, st); L.members.ensure(nc * AGG, st);
-    LAUNCH(c, k_agg_from_perm, grid_for(nc * AGG, TB), TB, 0, perm.p, nv, L.agg.p, L.members.p, nc * AGG);
-    lohi.release(st); code.release(st); codes.release(st); idx.release(st); perm.release(st);
+    LAUNCH(c, k_agg_from_perm, grid_for(nc * AGG, TB), TB, 0, perm, nv, L.agg.p, L.members.p, nc * AGG);
   }
   // ---- coarser levels by Galerkin products until the level is small enough for a dense inverse
-  while (c->amg.back().n > COARSEST && (int)c->amg.size() < MAXLEV) {
-    c->amg.emplace_back();
-    Ctx::AmgLevel& F = c->amg[c->amg.size() - 2];
-    Ctx::AmgLevel& C = c->amg.back();
+  while (c->amg[nlev - 1].n > COARSEST && nlev < MAXLEV) {
+    if ((int)c->amg.size() <= nlev) c->amg.emplace_back();
+    Ctx::AmgLevel& F = c->amg[nlev - 1];
+    Ctx::AmgLevel& C = c->amg[nlev];
+    nlev++;
     const int64_t nc = (F.n + AGG - 1) / AGG;
     C.n = nc;
-    DBuf<uint64_t> keys, keys2, ukeys;
-    DBuf<double> vals, vals2, uvals;
-    DBuf<int64_t> nruns;
-    keys.ensure(F.nnz, st); keys2.ensure(F.nnz, st); ukeys.ensure(F.nnz, st);
-    vals.ensure(F.nnz, st); vals2.ensure(F.nnz, st); uvals.ensure(F.nnz, st); nruns.ensure(1, st);
-    LAUNCH(c, k_galerkin_pairs, grid_for(F.n, TB), TB, 0, F.rowptr.p, F.col.p, F.val.p, F.agg.p, F.dinv.p, F.n, keys.p, vals.p);
-    size_t bytes = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys.p, keys2.p, vals.p, vals2.p, F.nnz, 0, 64, st));
+    uint64_t* keys = scratch<uint64_t>(c, 0, F.nnz);
+    uint64_t* keys2 = scratch<uint64_t>(c, 1, F.nnz);
+    uint64_t* ukeys = scratch<uint64_t>(c, 6, F.nnz);
+    double* vals = scratch<double>(c, 2, F.nnz);
+    double* vals2 = scratch<double>(c, 3, F.nnz);
+    double* uvals = scratch<double>(c, 7, F.nnz);
+    int64_t* nruns = scratch<int64_t>(c, 9, 2);
+    // level 0 carries its Morton aggregate map; deeper levels aggregate 8 consecutive rows (agg == nullptr)
+    const int32_t* aggmap = (nlev == 2) ? F.agg.p : (const int32_t*)nullptr;
+    LAUNCH(c, k_galerkin_pairs, grid_for(F.n, TB), TB, 0, F.rowptr.p, F.col.p, F.val.p, aggmap, F.dinv.p, F.n, keys, vals);
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys, keys2, vals, vals2, F.nnz, 0, 64, st));
     c->tmp.ensure(bytes, st);
-    CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, keys.p, keys2.p, vals.p, vals2.p, F.nnz, 0, 64, st));
-    CK(cub::DeviceReduce::ReduceByKey(nullptr, bytes, keys2.p, ukeys.p, vals2.p, uvals.p, nruns.p, cub::Sum(), F.nnz, st));
+    CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, keys, keys2, vals, vals2, F.nnz, 0, 64, st));
+    CK(cub::DeviceReduce::ReduceByKey(nullptr, bytes, keys2, ukeys, vals2, uvals, nruns, cub::Sum(), F.nnz, st));
     c->tmp.ensure(bytes, st);
-    CK(cub::DeviceReduce::ReduceByKey(c->tmp.p, bytes, keys2.p, ukeys.p, vals2.p, uvals.p, nruns.p, cub::Sum(), F.nnz, st));
+    CK(cub::DeviceReduce::ReduceByKey(c->tmp.p, bytes, keys2, ukeys, vals2, uvals, nruns, cub::Sum(), F.nnz, st));
     c->launches += 8;
     int64_t hr = 0;
     uint64_t lastkey = 0;
-    CK(cudaMemcpyAsync(&hr, nruns.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&hr, nruns, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (hr > 0) {
-      CK(cudaMemcpyAsync(&lastkey, ukeys.p + (hr - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(&lastkey, ukeys + (hr - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       if (lastkey == ~0ull) hr--;  // the run of dropped (constrained) entries
     }
     C.nnz = hr;
     C.rowptr.ensure(nc + 1, st); C.col.ensure(std::max<int64_t>(hr, 1), st); C.val.ensure(std::max<int64_t>(hr, 1), st); C.dinv.ensure(nc, st);
-    LAUNCH(c, k_coarse_rowptr, grid_for(nc + 1, TB), TB, 0, ukeys.p, hr, nc, C.rowptr.p);
+    LAUNCH(c, k_coarse_rowptr, grid_for(nc + 1, TB), TB, 0, ukeys, hr, nc, C.rowptr.p);
     if (hr) {
-      LAUNCH(c, k_coarse_cols, grid_for(hr, TB), TB, 0, ukeys.p, hr, C.col.p);
-      CK(cudaMemcpyAsync(C.val.p, uvals.p, hr * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      LAUNCH(c, k_coarse_cols, grid_for(hr, TB), TB, 0, ukeys, hr, C.col.p);
+      CK(cudaMemcpyAsync(C.val.p, uvals, hr * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
     LAUNCH(c, k_level_dinv, grid_for(nc, TB), TB, 0, C.rowptr.p, C.col.p, C.val.p, (const uint8_t*)nullptr, nc, C.dinv.p);
-    keys.release(st); keys2.release(st); ukeys.release(st); vals.release(st); vals2.release(st); uvals.release(st); nruns.release(st);
   }
-  for (auto& L : c->amg) L.omega = c->amg_omega_scale;  // l1-Jacobi: any weight <= 1 keeps the cycle SPD
+  c->amg_nlev = nlev;
+  for (int l = 0; l < nlev; l++) c->amg[l].omega = c->amg_omega_scale;  // l1-Jacobi: any weight <= 1 keeps the cycle SPD
   // ---- dense inverse of the coarsest level
   {
-    Ctx::AmgLevel& L = c->amg.back();
+    Ctx::AmgLevel& L = c->amg[nlev - 1];
     const int n = (int)L.n;
     if (n > 2048) FAIL(REMO_ERR_ARG, "amg_setup: coarsest level still has %d rows", n);
-    DBuf<double> M;
-    M.ensure((size_t)n * 2 * n, st);
+    double* M = scratch<double>(c, 6, (size_t)n * 2 * n);
     c->amg_dense.ensure((size_t)n * n, st);
-    LAUNCH(c, k_dense_fill, 1, 1024, 0, L.rowptr.p, L.col.p, L.val.p, n, M.p);
-    LAUNCH(c, k_dense_invert, 1, 1024, n * sizeof(double), n, M.p);
-    LAUNCH(c, k_dense_extract, 64, 256, 0, n, M.p, c->amg_dense.p);
-    M.release(st);
+    LAUNCH(c, k_dense_fill, 1, 1024, 0, L.rowptr.p, L.col.p, L.val.p, n, M);
+    LAUNCH(c, k_dense_invert, 1, 1024, n * sizeof(double), n, M);
+    LAUNCH(c, k_dense_extract, 64, 256, 0, n, M, c->amg_dense.p);
   }
 }
 
@@ -451,11 +454,12 @@ void amg_apply(Ctx* c, const double* R, double* Z, int k) {
   cudaStream_t st = c->stream;
   const double alpha = c->amg_alpha;
   const int sweeps = c->amg_sweeps;
-  const int nl = (int)c->amg.size();
-  if (c->amg_nrhs != k) {
-    for (auto& L : c->amg) { L.b.ensure(L.n * k, st); L.x.ensure(L.n * k, st); L.t.ensure(L.n * k, st); }
-    c->amg_nrhs = k;
+  const int nl = c->amg_nlev;
+  for (int l = 0; l < nl; l++) {  // grow-only: a no-op once the buffers are large enough
+    Ctx::AmgLevel& L = c->amg[l];
+    L.b.ensure(L.n * k, st); L.x.ensure(L.n * k, st); L.t.ensure(L.n * k, st);
   }
+  c->amg_nrhs = k;
   // down
   for (int l = 0; l < nl - 1; l++) {
     Ctx::AmgLevel& L = c->amg[l];

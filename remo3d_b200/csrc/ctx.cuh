@@ -123,6 +123,7 @@ struct Ctx {
   int amg_gamma = 1;                               // cycle index: 1 = V, 2 = W
   DBuf<double> amg_dense;     // inverse of the coarsest matrix (n x n)
   int amg_nrhs = 0;
+  int amg_nlev = 0;           // levels in use (the vector keeps its buffers across meshes)
 
   // ---- right-hand sides / PCG state, row-major ndof x nrhs
   int nrhs = 0;
@@ -138,10 +139,18 @@ struct Ctx {
   double prof_spmm_ms = 0.0;
   int64_t prof_spmm_n = 0;
 
-  // ---- scratch
+  // ---- scratch: grow-only slots reused by every phase (no per-mesh cudaMallocAsync / cudaFreeAsync churn: freeing and
+  //      re-allocating multi-GB temporaries through the pool costs 50-1500 ms at random, measured)
+  DBuf<uint8_t> scr[10];
   DBuf<uint8_t> tmp;  // CUB temp storage
   std::vector<double> host_scal;
 };
+
+template <typename T>
+static inline T* scratch(Ctx* c, int slot, size_t count) {
+  c->scr[slot].ensure(count * sizeof(T) + 16, c->stream);
+  return reinterpret_cast<T*>(c->scr[slot].p);
+}
 
 // ---- launch helper: counts launches (bench.py gpu_launches) and checks the launch
 #define LAUNCH(ctx, kern, grid, block, smem, ...)                      \

@@ -187,27 +187,22 @@ int bits_for(uint64_t n) {
 
 // sort (key,payload) pairs, number the distinct keys 0.. in ascending order; returns the count
 template <typename KeyT>
-int64_t sort_and_number(Ctx* c, DBuf<KeyT>& keys, DBuf<uint32_t>& pay, int64_t n, int end_bit, DBuf<KeyT>& keys_sorted,
-                        DBuf<uint32_t>& pay_sorted) {
-  keys_sorted.ensure(n, c->stream);
-  pay_sorted.ensure(n, c->stream);
+void sort_pairs(Ctx* c, const KeyT* keys, const uint32_t* pay, int64_t n, int end_bit, KeyT* keys_sorted, uint32_t* pay_sorted) {
   size_t bytes = 0;
-  CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys.p, keys_sorted.p, pay.p, pay_sorted.p, n, 0, end_bit, c->stream));
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys, keys_sorted, pay, pay_sorted, n, 0, end_bit, c->stream));
   c->tmp.ensure(bytes, c->stream);
-  CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, keys.p, keys_sorted.p, pay.p, pay_sorted.p, n, 0, end_bit, c->stream));
+  CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, keys, keys_sorted, pay, pay_sorted, n, 0, end_bit, c->stream));
   c->launches += 4;
-  return n;
 }
 
-int32_t scan_flags(Ctx* c, DBuf<int32_t>& flag, DBuf<int32_t>& scan, int64_t n) {
-  scan.ensure(n, c->stream);
+int32_t scan_flags(Ctx* c, const int32_t* flag, int32_t* scan, int64_t n) {
   size_t bytes = 0;
-  CK(cub::DeviceScan::InclusiveSum(nullptr, bytes, flag.p, scan.p, n, c->stream));
+  CK(cub::DeviceScan::InclusiveSum(nullptr, bytes, flag, scan, n, c->stream));
   c->tmp.ensure(bytes, c->stream);
-  CK(cub::DeviceScan::InclusiveSum(c->tmp.p, bytes, flag.p, scan.p, n, c->stream));
+  CK(cub::DeviceScan::InclusiveSum(c->tmp.p, bytes, flag, scan, n, c->stream));
   c->launches += 2;
   int32_t total = 0;
-  CK(cudaMemcpyAsync(&total, scan.p + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&total, scan + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return total;
 }
@@ -239,37 +234,42 @@ void space_build(Ctx* c, int order) {
   c->sv.ensure(nt * nvl, st);
   LAUNCH(c, k_sort_verts, grid_for(nt, TB), TB, 0, c->elems.p, c->sv.p, nt, nvl);
 
-  DBuf<uint64_t> k64, k64s;
-  DBuf<uint32_t> pay, pays;
-  DBuf<int32_t> flag, scan;
+  // scratch slots: 0 keys, 1 sorted keys, 2 payload, 3 sorted payload, 4 flags, 5 scan, 6/7 candidate columns
+  const int64_t nadj = nt * c->nld;
+  const int64_t ncand = nadj * c->nld;
+  if (nadj >= (int64_t)1 << 32) FAIL(REMO_ERR_ARG, "remo_space_build: mesh too large (nt*nld >= 2^32)");
+  if (ncand >= (int64_t)1 << 31) FAIL(REMO_ERR_ARG, "remo_space_build: %lld candidate entries exceed the 2^31 limit of the pattern builder", (long long)ncand);
+  const int64_t nkeys = std::max<int64_t>(nt * c->nle, nt * 4);
+  uint64_t* k64 = scratch<uint64_t>(c, 0, std::max<int64_t>(nkeys, (nadj + 1) / 2));
+  uint64_t* k64s = scratch<uint64_t>(c, 1, std::max<int64_t>(nkeys, (nadj + 1) / 2));
+  uint32_t* pay = scratch<uint32_t>(c, 2, std::max(nkeys, nadj));
+  uint32_t* pays = scratch<uint32_t>(c, 3, std::max(nkeys, nadj));
+  int32_t* flag = scratch<int32_t>(c, 4, std::max(nkeys, ncand));
+  int32_t* scan = scratch<int32_t>(c, 5, std::max(nkeys, ncand));
 
   // 2. edges (always built: order >= 2 needs the dofs, order 1 needs nothing but the cost is small and
   //    remo_topology_get exports them)
   {
     const int64_t n = nt * c->nle;
-    k64.ensure(n, st); pay.ensure(n, st);
-    LAUNCH(c, k_edge_keys, grid_for(n, TB), TB, 0, c->sv.p, k64.p, pay.p, nt, nvl, c->nle);
-    sort_and_number(c, k64, pay, n, 32 + bits_for((uint64_t)c->nv), k64s, pays);
-    flag.ensure(n, st);
-    LAUNCH(c, k_flag_first, grid_for(n, TB), TB, 0, k64s.p, flag.p, n);
+    LAUNCH(c, k_edge_keys, grid_for(n, TB), TB, 0, c->sv.p, k64, pay, nt, nvl, c->nle);
+    sort_pairs(c, k64, pay, n, 32 + bits_for((uint64_t)c->nv), k64s, pays);
+    LAUNCH(c, k_flag_first, grid_for(n, TB), TB, 0, k64s, flag, n);
     c->ne = scan_flags(c, flag, scan, n);
     c->edge_keys.ensure(c->ne, st);
     c->elem_edges.ensure(n, st);
-    LAUNCH(c, k_assign_ids, grid_for(n, TB), TB, 0, k64s.p, pays.p, scan.p, c->elem_edges.p, c->edge_keys.p, n);
+    LAUNCH(c, k_assign_ids, grid_for(n, TB), TB, 0, k64s, pays, scan, c->elem_edges.p, c->edge_keys.p, n);
   }
   // 3. faces (3D order 3 only); in 2D the order-3 cell bubbles are numbered by element
   c->nf = 0;
   if (order == 3 && dim == 3) {
     const int64_t n = nt * 4;
-    k64.ensure(n, st); pay.ensure(n, st);
-    LAUNCH(c, k_face_keys, grid_for(n, TB), TB, 0, c->sv.p, c->elem_edges.p, k64.p, pay.p, nt);
-    sort_and_number(c, k64, pay, n, 32 + bits_for((uint64_t)c->ne), k64s, pays);
-    flag.ensure(n, st);
-    LAUNCH(c, k_flag_first, grid_for(n, TB), TB, 0, k64s.p, flag.p, n);
+    LAUNCH(c, k_face_keys, grid_for(n, TB), TB, 0, c->sv.p, c->elem_edges.p, k64, pay, nt);
+    sort_pairs(c, k64, pay, n, 32 + bits_for((uint64_t)c->ne), k64s, pays);
+    LAUNCH(c, k_flag_first, grid_for(n, TB), TB, 0, k64s, flag, n);
     c->nf = scan_flags(c, flag, scan, n);
     c->face_keys.ensure(c->nf, st);
     c->elem_faces.ensure(n, st);
-    LAUNCH(c, k_assign_ids, grid_for(n, TB), TB, 0, k64s.p, pays.p, scan.p, c->elem_faces.p, c->face_keys.p, n);
+    LAUNCH(c, k_assign_ids, grid_for(n, TB), TB, 0, k64s, pays, scan, c->elem_faces.p, c->face_keys.p, n);
   } else if (order == 3 && dim == 2) {
     c->nf = nt;
   }
@@ -277,78 +277,59 @@ void space_build(Ctx* c, int order) {
   c->face_base = c->nv + (int64_t)(order - 1) * c->ne;
   c->ndof = c->face_base + (order == 3 ? c->nf : 0);
   if (c->ndof >= (int64_t)1 << 31) FAIL(REMO_ERR_ARG, "remo_space_build: %lld dofs exceed the int32 column index", (long long)c->ndof);
-  k64.release(st); k64s.release(st);
 
   SpaceView sview = make_view(c);
+  int* bad = scratch<int>(c, 8, 4);
 
   // 4. Dirichlet dofs
   c->constrained.ensure(c->ndof, st);
   CK(cudaMemsetAsync(c->constrained.p, 0, c->ndof, st));
   if (c->nb > 0) {
-    DBuf<int> bad;
-    bad.ensure(1, st);
-    CK(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
-    LAUNCH(c, k_mark_dirichlet, grid_for(c->nb, TB), TB, 0, sview, c->bfacets.p, c->bdir.p, c->nb, c->constrained.p, bad.p);
+    CK(cudaMemsetAsync(bad, 0, sizeof(int), st));
+    LAUNCH(c, k_mark_dirichlet, grid_for(c->nb, TB), TB, 0, sview, c->bfacets.p, c->bdir.p, c->nb, c->constrained.p, bad);
     int hbad = 0;
-    CK(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    bad.release(st);
     if (hbad) FAIL(REMO_ERR_MESH, "remo_space_build: a Dirichlet boundary facet is not a face of the mesh");
   }
 
   // 5. dof -> (element, local dof) adjacency, elements ascending within a dof (stable radix sort)
-  const int64_t nadj = nt * c->nld;
-  if (nadj >= (int64_t)1 << 32) FAIL(REMO_ERR_ARG, "remo_space_build: mesh too large (nt*nld >= 2^32)");
   c->nadj = nadj;
-  DBuf<uint32_t> akey, akeys;
-  akey.ensure(nadj, st); pay.ensure(nadj, st);
-  LAUNCH(c, k_adj_pairs, grid_for(nadj, TB), TB, 0, sview, akey.p, pay.p, nadj);
+  uint32_t* akey = reinterpret_cast<uint32_t*>(k64);
+  uint32_t* akeys = reinterpret_cast<uint32_t*>(k64s);
+  LAUNCH(c, k_adj_pairs, grid_for(nadj, TB), TB, 0, sview, akey, pay, nadj);
   c->adj.ensure(nadj, st);
-  {
-    akeys.ensure(nadj, st);
-    size_t bytes = 0;
-    const int eb = bits_for((uint64_t)c->ndof);
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, akey.p, akeys.p, pay.p, c->adj.p, nadj, 0, eb, st));
-    c->tmp.ensure(bytes, st);
-    CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, akey.p, akeys.p, pay.p, c->adj.p, nadj, 0, eb, st));
-    c->launches += 4;
-  }
-  akey.release(st); pay.release(st); pays.release(st);
+  sort_pairs(c, akey, pay, nadj, bits_for((uint64_t)c->ndof), akeys, c->adj.p);
   c->adj_ptr.ensure(c->ndof + 1, st);
-  LAUNCH(c, k_adj_ptr, grid_for(nadj + 1, TB), TB, 0, akeys.p, nadj, c->ndof, c->adj_ptr.p);
+  LAUNCH(c, k_adj_ptr, grid_for(nadj + 1, TB), TB, 0, akeys, nadj, c->ndof, c->adj_ptr.p);
 
   // 6. CSR pattern: per row sort + unique of the candidate columns
-  const int64_t ncand = nadj * c->nld;
-  if (ncand >= (int64_t)1 << 31) FAIL(REMO_ERR_ARG, "remo_space_build: %lld candidate entries exceed the 2^31 limit of the pattern builder", (long long)ncand);
-  DBuf<int32_t> cand, cands;
-  cand.ensure(ncand, st); cands.ensure(ncand, st);
-  LAUNCH(c, k_candidates, grid_for(ncand, TB), TB, 0, sview, c->adj.p, cand.p, nadj);
+  int32_t* cand = scratch<int32_t>(c, 6, ncand);
+  int32_t* cands = scratch<int32_t>(c, 7, ncand);
+  LAUNCH(c, k_candidates, grid_for(ncand, TB), TB, 0, sview, c->adj.p, cand, nadj);
   {
     cub::CountingInputIterator<int64_t> cnt(0);
     cub::TransformInputIterator<int64_t, ScaleOffsets, cub::CountingInputIterator<int64_t>> begins(cnt, ScaleOffsets{c->adj_ptr.p, c->nld});
     size_t bytes = 0;
-    CK(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, cand.p, cands.p, (int)ncand, (int)c->ndof, begins, begins + 1, st));
+    CK(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, cand, cands, (int)ncand, (int)c->ndof, begins, begins + 1, st));
     c->tmp.ensure(bytes, st);
-    CK(cub::DeviceSegmentedSort::SortKeys(c->tmp.p, bytes, cand.p, cands.p, (int)ncand, (int)c->ndof, begins, begins + 1, st));
+    CK(cub::DeviceSegmentedSort::SortKeys(c->tmp.p, bytes, cand, cands, (int)ncand, (int)c->ndof, begins, begins + 1, st));
     c->launches += 4;
   }
-  cand.release(st);
-  flag.ensure(ncand, st);
-  LAUNCH(c, k_flag_cols, grid_for(ncand, TB), TB, 0, cands.p, akeys.p, c->nld, flag.p, ncand);
+  LAUNCH(c, k_flag_cols, grid_for(ncand, TB), TB, 0, cands, akeys, c->nld, flag, ncand);
   c->nnz = scan_flags(c, flag, scan, ncand);
   c->rowptr.ensure(c->ndof + 1, st);
   c->col.ensure(c->nnz, st);
   c->val.ensure(c->nnz, st);
-  LAUNCH(c, k_fill_csr, grid_for(ncand, TB), TB, 0, cands.p, akeys.p, c->nld, scan.p, ncand, c->rowptr.p, c->col.p);
+  LAUNCH(c, k_fill_csr, grid_for(ncand, TB), TB, 0, cands, akeys, c->nld, scan, ncand, c->rowptr.p, c->col.p);
   {
     // rows after the last one that has elements (and the terminating entry)
     uint32_t last = 0;
-    CK(cudaMemcpyAsync(&last, akeys.p + (nadj - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&last, akeys + (nadj - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     int64_t from = (int64_t)last + 1;
     LAUNCH(c, k_fill_tail, grid_for(c->ndof + 1 - from, TB), TB, 0, c->rowptr.p, from, c->ndof, c->nnz);
   }
-  cands.release(st); flag.release(st); scan.release(st); akeys.release(st);
   c->have_space = true;
 }
 
