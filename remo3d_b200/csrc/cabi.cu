@@ -233,7 +233,7 @@ int remo_rhs_point_sources(void* vctx, int nrhs, const int64_t* src_ptr, const d
 }
 
 static int get_column(Ctx* c, const double* block, int rhs, double* out, const char* who) {
-  if (rhs < 0 || rhs >= c->nrhs || !out) FAIL(REMO_ERR_ARG, "%s: right-hand-side index out of range", who);
+  if (rhs < 0 || rhs >= c->nrhs_user || !out) FAIL(REMO_ERR_ARG, "%s: right-hand-side index out of range", who);
   DBuf<double> t;
   t.ensure(c->ndof, c->stream);
   LAUNCH(c, k_extract_col, grid_for(c->ndof, 256), 256, 0, block, c->ndof, c->nrhs, rhs, t.p);
@@ -284,24 +284,25 @@ int remo_kernel_time(void* vctx, int which, int nrhs, int reps, float* ms) {
     if (reps < 1 || !ms || nrhs < 1 || nrhs > REMO_MAX_RHS) FAIL(REMO_ERR_ARG, "remo_kernel_time: bad arguments");
     cudaStream_t st = c->stream;
     if (which == 0 || which == 2) {
-      if (c->nrhs != nrhs || !c->have_rhs) {
+      if (c->nrhs_user != nrhs || !c->have_rhs) {
         alloc_solver_state(c, nrhs);
+        c->nrhs_user = nrhs;
         CK(cudaMemsetAsync(c->F.p, 0, (size_t)c->ndof * nrhs * sizeof(double), st));
         c->have_rhs = true;
         c->have_solution = false;
       }
       if (c->pkind < 0) precond_setup(c, REMO_PRECOND_LOCAL);
       // deterministic non-trivial vectors: P = dinv-scaled ones pattern is not needed for timing; reuse F
-      CK(cudaMemcpyAsync(c->P.p, c->F.p, (size_t)c->ndof * nrhs * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(c->P.p, c->F.p, (size_t)c->ndof * c->nrhs * sizeof(double), cudaMemcpyDeviceToDevice, st));
       CK(cudaMemsetAsync(c->scal.p, 0, c->scal.n * sizeof(double), st));
     }
     cudaEvent_t a, b;
     CK(cudaEventCreate(&a));
     CK(cudaEventCreate(&b));
     auto body = [&]() {
-      if (which == 0) launch_spmm(c, c->P.p, c->Q.p, nrhs);
+      if (which == 0) launch_spmm(c, c->P.p, c->Q.p, c->nrhs);  // internal (even) stride
       else if (which == 1) assemble_kernels_only(c);
-      else launch_vector_updates(c, nrhs);
+      else launch_vector_updates(c, c->nrhs);
     };
     body();  // warm-up
     CK(cudaEventRecord(a, st));

@@ -126,7 +126,8 @@ struct Ctx {
   int amg_nlev = 0;           // levels in use (the vector keeps its buffers across meshes)
 
   // ---- right-hand sides / PCG state, row-major ndof x nrhs
-  int nrhs = 0;
+  int nrhs = 0;       // internal column count = row stride of the vector blocks (user count rounded up to even)
+  int nrhs_user = 0;  // right-hand sides the caller asked for
   DBuf<double> F, X, R, Z, P, Q;
   DBuf<double> partial;  // per-block partial dot products
   DBuf<double> scal;     // device scalars, see solver.cu

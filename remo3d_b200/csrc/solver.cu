@@ -138,6 +138,74 @@ __global__ void __launch_bounds__(TB) k_spmm_g(const int64_t* __restrict__ rowpt
 }
 
 // ------------------------------------------------------------------------------------------------
+// Variant 4 (default for nrhs >= 2): as variant 3, but every lane owns TWO adjacent right-hand sides and gathers them
+// with one 16-byte load (the row stride of the vector blocks is kept even for this).  An entry then needs KP2 = ks/2
+// lanes instead of ks, a 4-lane group owns a row (8 rows in flight per warp) and one shuffle serves twice as many
+// matrix entries: the L1 data-pipe cost per entry (profiles/r01_notes.md) drops from ~2.45 to ~2.0 wavefronts.
+// ------------------------------------------------------------------------------------------------
+template <int G, int KP2>
+__global__ void __launch_bounds__(TB) k_spmm_p(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                               const double* __restrict__ val, const uint8_t* __restrict__ constrained,
+                                               const double* __restrict__ P, double* __restrict__ Q, int ks, int64_t n,
+                                               double* __restrict__ partial) {
+  constexpr int J = G / KP2;
+  constexpr int GROUPS = TB / G;
+  const int lane = threadIdx.x & 31;
+  const int gl = threadIdx.x % G, grp = threadIdx.x / G;
+  const int jsub = gl / KP2, r2 = gl % KP2;
+  const bool on = 2 * r2 < ks;
+  const int cc = on ? 2 * r2 : 0;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((lane / G) * G));
+  double dot0 = 0.0, dot1 = 0.0;
+  for (int64_t row = (int64_t)blockIdx.x * GROUPS + grp; row < n; row += (int64_t)gridDim.x * GROUPS) {
+    const int64_t s = rowptr[row], e = rowptr[row + 1];
+    double acc0 = 0.0, acc1 = 0.0;
+    int32_t nc = (int32_t)row;
+    double nv = 0.0;
+    if (s + gl < e) { nc = __ldg(col + s + gl); nv = __ldg(val + s + gl); }
+    for (int64_t base = s; base < e; base += G) {
+      const int32_t myc = nc;
+      const double myv = nv;
+      nc = (int32_t)row; nv = 0.0;
+      if (base + G + gl < e) { nc = __ldg(col + base + G + gl); nv = __ldg(val + base + G + gl); }
+      double2 x[KP2];
+      double vv[KP2];
+#pragma unroll
+      for (int i = 0; i < KP2; i++) {
+        const int j = i * J + jsub;
+        const int32_t c = __shfl_sync(gmask, myc, j, G);
+        vv[i] = __shfl_sync(gmask, myv, j, G);
+        x[i] = *reinterpret_cast<const double2*>(P + (int64_t)c * ks + cc);
+      }
+#pragma unroll
+      for (int i = 0; i < KP2; i++) { acc0 = fma(vv[i], x[i].x, acc0); acc1 = fma(vv[i], x[i].y, acc1); }
+    }
+#pragma unroll
+    for (int o = G / 2; o >= KP2; o >>= 1) {
+      acc0 += __shfl_xor_sync(gmask, acc0, o, G);
+      acc1 += __shfl_xor_sync(gmask, acc1, o, G);
+    }
+    if (constrained[row]) { acc0 = 0.0; acc1 = 0.0; }
+    if (jsub == 0 && on) {
+      const double2 p = *reinterpret_cast<const double2*>(P + row * ks + cc);
+      *reinterpret_cast<double2*>(Q + row * ks + cc) = make_double2(acc0, acc1);
+      dot0 = fma(acc0, p.x, dot0);
+      dot1 = fma(acc1, p.y, dot1);
+    }
+  }
+  __shared__ double sh[2][TB];
+  sh[0][threadIdx.x] = (jsub == 0 && on) ? dot0 : 0.0;
+  sh[1][threadIdx.x] = (jsub == 0 && on) ? dot1 : 0.0;
+  __syncthreads();
+  if (threadIdx.x < KP2 && 2 * threadIdx.x < ks) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int i = threadIdx.x; i < TB; i += G) { t0 += sh[0][i]; t1 += sh[1][i]; }
+    partial[(int64_t)blockIdx.x * KMAX + 2 * threadIdx.x] = t0;
+    partial[(int64_t)blockIdx.x * KMAX + 2 * threadIdx.x + 1] = t1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // vector kernels: thread = (row group, r) with r = threadIdx % KP
 // ------------------------------------------------------------------------------------------------
 template <int KP>
@@ -337,7 +405,7 @@ __global__ void k_dinv(const int64_t* __restrict__ rowptr, const int32_t* __rest
 // ------------------------------------------------------------------------------------------------
 // point sources, sampling, apparent resistivity
 // ------------------------------------------------------------------------------------------------
-__global__ void k_point_sources(SpaceView s, int nrhs, const int64_t* __restrict__ src_ptr, const double* __restrict__ src_z,
+__global__ void k_point_sources(SpaceView s, int nrhs, int stride, const int64_t* __restrict__ src_ptr, const double* __restrict__ src_z,
                                 const double* __restrict__ src_fac, double* __restrict__ F, int* __restrict__ bad) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nrhs) return;
@@ -348,7 +416,7 @@ __global__ void k_point_sources(SpaceView s, int nrhs, const int64_t* __restrict
     double val[4];
     const int m = axis_shape(s, src_z[i], dof, val);
     if (m <= 0) { atomicExch(bad, m == 0 ? 1 : 2); continue; }
-    for (int q = 0; q < m; q++) F[dof[q] * nrhs + r] += fac * val[q];  // one thread per column: no race
+    for (int q = 0; q < m; q++) F[dof[q] * stride + r] += fac * val[q];  // one thread per column: no race
   }
 }
 
@@ -363,22 +431,22 @@ __device__ __forceinline__ double eval_axis(const SpaceView& s, const double* __
   return u;
 }
 
-__global__ void k_sample(SpaceView s, const double* __restrict__ X, int nrhs, int npts, const int32_t* __restrict__ pt_rhs,
+__global__ void k_sample(SpaceView s, const double* __restrict__ X, int nrhs, int nuser, int npts, const int32_t* __restrict__ pt_rhs,
                          const double* __restrict__ z, double* __restrict__ out, int* __restrict__ bad) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npts) return;
   const int rhs = pt_rhs ? pt_rhs[i] : 0;
-  if (rhs < 0 || rhs >= nrhs) { atomicExch(bad, 3); out[i] = nan(""); return; }
+  if (rhs < 0 || rhs >= nuser) { atomicExch(bad, 3); out[i] = nan(""); return; }
   out[i] = eval_axis(s, X, nrhs, rhs, z[i], bad);
 }
 
-__global__ void k_resistivity(SpaceView s, const double* __restrict__ X, int nrhs, int npts, const int32_t* __restrict__ pt_rhs,
+__global__ void k_resistivity(SpaceView s, const double* __restrict__ X, int nrhs, int nuser, int npts, const int32_t* __restrict__ pt_rhs,
                               const double* __restrict__ z0, const double* __restrict__ z1, const double* __restrict__ kf,
                               double scale, double* __restrict__ ra, int* __restrict__ bad) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npts) return;
   const int rhs = pt_rhs[i];
-  if (rhs < 0 || rhs >= nrhs) { atomicExch(bad, 3); ra[i] = nan(""); return; }
+  if (rhs < 0 || rhs >= nuser) { atomicExch(bad, 3); ra[i] = nan(""); return; }
   const double u0 = eval_axis(s, X, nrhs, rhs, z0[i], bad);
   double du = u0;
   if (z1[i] == z1[i]) du = eval_axis(s, X, nrhs, rhs, z1[i], bad) - u0;
@@ -432,7 +500,7 @@ static int spmm_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("REMO_SPMM_VARIANT");
-    v = e ? atoi(e) : 3;
+    v = e ? atoi(e) : 4;
   }
   return v;
 }
@@ -440,7 +508,21 @@ static int spmm_variant() {
 void launch_spmm(Ctx* c, const double* P, double* Q, int nrhs) {
   const int kp = kp_for(nrhs);
   const int grid = spmm_grid(c);
-  if (spmm_variant() == 3) {
+  if (spmm_variant() >= 3 && (nrhs & 1) == 0) {  // even stride: paired-column kernel
+    auto* rp = c->rowptr.p; auto* cl = c->col.p; auto* vl = c->val.p; auto* cs = c->constrained.p;
+    double* pt = c->partial.p;
+    const int64_t n = c->ndof;
+    cudaStream_t st = c->stream;
+    if (nrhs <= 2) k_spmm_p<4, 1><<<grid, TB, 0, st>>>(rp, cl, vl, cs, P, Q, nrhs, n, pt);
+    else if (nrhs <= 4) k_spmm_p<4, 2><<<grid, TB, 0, st>>>(rp, cl, vl, cs, P, Q, nrhs, n, pt);
+    else if (nrhs <= 8) k_spmm_p<4, 4><<<grid, TB, 0, st>>>(rp, cl, vl, cs, P, Q, nrhs, n, pt);
+    else if (nrhs <= 16) k_spmm_p<8, 8><<<grid, TB, 0, st>>>(rp, cl, vl, cs, P, Q, nrhs, n, pt);
+    else k_spmm_p<16, 16><<<grid, TB, 0, st>>>(rp, cl, vl, cs, P, Q, nrhs, n, pt);
+    c->launches++;
+    CK(cudaGetLastError());
+    return;
+  }
+  if (spmm_variant() >= 3) {
     auto* rp = c->rowptr.p; auto* cl = c->col.p; auto* vl = c->val.p; auto* cs = c->constrained.p;
     double* pt = c->partial.p;
     const int64_t n = c->ndof;
@@ -486,7 +568,11 @@ void rhs_point_sources(Ctx* c, int nrhs, const int64_t* src_ptr, const double* s
   if (nrhs < 1 || nrhs > REMO_MAX_RHS) FAIL(REMO_ERR_ARG, "remo_rhs_point_sources: nrhs must be in 1..%d (got %d)", REMO_MAX_RHS, nrhs);
   StageTimer timer(c, ST_RHS);
   cudaStream_t st = c->stream;
-  alloc_solver_state(c, nrhs);
+  // row stride of the vector blocks: even (the SpMM gathers two right-hand sides per 16-byte load); the extra column
+  // of an odd count has b = 0 and is frozen from the first iteration
+  const int ks = (nrhs > 1 && spmm_variant() >= 4) ? ((nrhs + 1) & ~1) : nrhs;
+  alloc_solver_state(c, ks);
+  c->nrhs_user = nrhs;
   std::vector<int64_t> hp(nrhs + 1);
   CK(cudaMemcpyAsync(hp.data(), src_ptr, (nrhs + 1) * sizeof(int64_t), cudaMemcpyDefault, st));
   CK(cudaStreamSynchronize(st));
@@ -502,8 +588,8 @@ void rhs_point_sources(Ctx* c, int nrhs, const int64_t* src_ptr, const double* s
     CK(cudaMemcpyAsync(df.p, src_fac, ns * sizeof(double), cudaMemcpyDefault, st));
   }
   CK(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
-  CK(cudaMemsetAsync(c->F.p, 0, (size_t)c->ndof * nrhs * sizeof(double), st));
-  LAUNCH(c, k_point_sources, 1, 32, 0, make_view(c), nrhs, dp.p, dz.p, df.p, c->F.p, bad.p);
+  CK(cudaMemsetAsync(c->F.p, 0, (size_t)c->ndof * ks * sizeof(double), st));
+  LAUNCH(c, k_point_sources, 1, 32, 0, make_view(c), nrhs, ks, dp.p, dz.p, df.p, c->F.p, bad.p);
   check_bad(c, bad, "remo_rhs_point_sources");
   dp.release(st); dz.release(st); df.release(st);
   c->have_rhs = true;
@@ -574,7 +660,7 @@ int solve(Ctx* c, double rtol, int maxit, int* iters, double* relres) {
   CK(cudaMemcpyAsync(hit.data(), c->iters_d.p, KMAX * sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   bool conv = true;
-  for (int r = 0; r < k; r++) {
+  for (int r = 0; r < c->nrhs_user; r++) {
     const double bb = hs[S_BB * KMAX + r], rr = hs[S_RR * KMAX + r];
     const double rel = bb > 0.0 ? sqrt(rr / bb) : 0.0;
     if (iters) iters[r] = hit[r];
@@ -607,7 +693,7 @@ void sample_axis(Ctx* c, int npts, const int32_t* pt_rhs, const double* z, doubl
   if (pt_rhs) CK(cudaMemcpyAsync(dr.p, pt_rhs, npts * sizeof(int32_t), cudaMemcpyDefault, st));
   CK(cudaMemcpyAsync(dz.p, z, npts * sizeof(double), cudaMemcpyDefault, st));
   CK(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
-  LAUNCH(c, k_sample, grid_for(npts, 128), 128, 0, make_view(c), c->X.p, c->nrhs, npts, pt_rhs ? dr.p : nullptr, dz.p, dout.p, bad.p);
+  LAUNCH(c, k_sample, grid_for(npts, 128), 128, 0, make_view(c), c->X.p, c->nrhs, c->nrhs_user, npts, pt_rhs ? dr.p : nullptr, dz.p, dout.p, bad.p);
   CK(cudaMemcpyAsync(out, dout.p, npts * sizeof(double), cudaMemcpyDefault, st));
   check_bad(c, bad, "remo_sample_axis");
   dr.release(st); dz.release(st); dout.release(st);
@@ -628,7 +714,7 @@ void apparent_resistivity(Ctx* c, int npts, const int32_t* pt_rhs, const double*
   CK(cudaMemcpyAsync(d1.p, z1, npts * sizeof(double), cudaMemcpyDefault, st));
   CK(cudaMemcpyAsync(dk.p, kf, npts * sizeof(double), cudaMemcpyDefault, st));
   CK(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
-  LAUNCH(c, k_resistivity, grid_for(npts, 128), 128, 0, make_view(c), c->X.p, c->nrhs, npts, dr.p, d0.p, d1.p, dk.p, scale, dout.p, bad.p);
+  LAUNCH(c, k_resistivity, grid_for(npts, 128), 128, 0, make_view(c), c->X.p, c->nrhs, c->nrhs_user, npts, dr.p, d0.p, d1.p, dk.p, scale, dout.p, bad.p);
   CK(cudaMemcpyAsync(ra, dout.p, npts * sizeof(double), cudaMemcpyDefault, st));
   check_bad(c, bad, "remo_apparent_resistivity");
   dr.release(st); d0.release(st); d1.release(st); dk.release(st); dout.release(st);
