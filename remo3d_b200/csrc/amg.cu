@@ -249,14 +249,6 @@ __global__ void k_prolong(const int32_t* __restrict__ agg, const double* __restr
   X[e] = fma(alpha, XC[a * k + r], X[e]);
 }
 
-// high-order dofs: z = dinv r for rows [n0, n)
-__global__ void k_diag_tail(const double* __restrict__ dinv, const double* __restrict__ R, double* __restrict__ Z, int k, int64_t n0,
-                            int64_t n) {
-  int64_t e = n0 * k + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e >= n * k) return;
-  Z[e] = dinv[e / k] * R[e];
-}
-
 // ---------------------------------------------------------------- coarsest level: dense inverse
 __global__ void k_dense_fill(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
                              int n, double* __restrict__ M) {  // M = [A | I], n x 2n
@@ -449,7 +441,7 @@ void amg_setup(Ctx* c) {
   }
 }
 
-// z_vert = V-cycle(r_vert), z_high = D^-1 r_high.  R, Z: ndof x k blocks of the PCG.
+// z_vert = V-cycle(r_vert) on the leading nv rows of the ndof x k blocks R, Z of the PCG.
 void amg_apply(Ctx* c, const double* R, double* Z, int k) {
   cudaStream_t st = c->stream;
   const double alpha = c->amg_alpha;
@@ -493,6 +485,5 @@ void amg_apply(Ctx* c, const double* R, double* Z, int k) {
       if (out == L.t.p) std::swap(L.x.p, L.t.p);
     }
   }
-  if (c->ndof > c->nv)
-    LAUNCH(c, k_diag_tail, grid_for((c->ndof - c->nv) * k, TB), TB, 0, c->dinv.p, R, Z, k, c->nv, c->ndof);
+  // the high-order rows (z = D^-1 r) are handled inside the PCG vector kernels (k_init / k_update_xr, tail_from = nv)
 }

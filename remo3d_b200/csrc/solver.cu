@@ -223,11 +223,11 @@ __device__ __forceinline__ void block_partials(double a, double b, double* __res
   }
 }
 
-// X = 0, R = masked F, (Jacobi) Z = dinv R, P = Z; partials: [0] = r.r (= b.b), [1] = r.z
+// X = 0, R = masked F, Z = dinv R and P = Z on rows >= tail_from; partials: [0] = r.r (= b.b), [1] = r.z over those rows
 template <int KP>
 __global__ void __launch_bounds__(TB) k_init(const double* __restrict__ F, const uint8_t* __restrict__ constrained,
                                              const double* __restrict__ dinv, double* __restrict__ X, double* __restrict__ R,
-                                             double* __restrict__ Z, double* __restrict__ P, int k, int64_t n, int jacobi,
+                                             double* __restrict__ Z, double* __restrict__ P, int k, int64_t n, int64_t tail_from,
                                              double* __restrict__ partial) {
   const int r = threadIdx.x % KP, g = threadIdx.x / KP;
   constexpr int G = TB / KP;
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(TB) k_init(const double* __restrict__ F, const
       X[idx] = 0.0;
       R[idx] = f;
       rr = fma(f, f, rr);
-      if (jacobi) {
+      if (i >= tail_from) {  // rows preconditioned by their diagonal: all rows ("local"), the high-order rows ("multigrid")
         const double z = dinv[i] * f;
         Z[idx] = z;
         P[idx] = z;
@@ -249,12 +249,12 @@ __global__ void __launch_bounds__(TB) k_init(const double* __restrict__ F, const
   block_partials<KP>(rr, rz, partial, 2);
 }
 
-// x += alpha p ; r -= alpha q ; (Jacobi) z = dinv r ; partials [0] = r.r, [1] = r.z
+// x += alpha p ; r -= alpha q ; z = dinv r on rows >= tail_from ; partials [0] = r.r, [1] = r.z over those rows
 template <int KP>
 __global__ void __launch_bounds__(TB) k_update_xr(double* __restrict__ X, double* __restrict__ R, const double* __restrict__ P,
                                                   const double* __restrict__ Q, const double* __restrict__ dinv,
                                                   double* __restrict__ Z, const double* __restrict__ scal, int k, int64_t n,
-                                                  int jacobi, double* __restrict__ partial) {
+                                                  int64_t tail_from, double* __restrict__ partial) {
   const int r = threadIdx.x % KP, g = threadIdx.x / KP;
   constexpr int G = TB / KP;
   double rr = 0.0, rz = 0.0;
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(TB) k_update_xr(double* __restrict__ X, double
       const double res = fma(-alpha, Q[idx], R[idx]);
       R[idx] = res;
       rr = fma(res, res, rr);
-      if (jacobi) {
+      if (i >= tail_from) {
         const double z = dinv[i] * res;
         Z[idx] = z;
         rz = fma(res, z, rz);
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(TB) k_update_xr(double* __restrict__ X, double
   block_partials<KP>(rr, rz, partial, 2);
 }
 
-// partial [1] = r.z for a general preconditioner
+// partial [1] += r.z over rows [0, n): the rows preconditioned by the V-cycle (the others were summed by k_update_xr)
 template <int KP>
 __global__ void __launch_bounds__(TB) k_dot_rz(const double* __restrict__ R, const double* __restrict__ Z, int k, int64_t n,
                                                double* __restrict__ partial) {
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(TB) k_dot_rz(const double* __restrict__ R, con
   if (threadIdx.x < KP) {
     double t = 0.0;
     for (int i = threadIdx.x; i < TB; i += KP) t += sh[i];
-    partial[((int64_t)blockIdx.x * 2 + 1) * KMAX + threadIdx.x] = t;
+    partial[((int64_t)blockIdx.x * 2 + 1) * KMAX + threadIdx.x] += t;
   }
 }
 
@@ -547,7 +547,7 @@ void launch_spmm(Ctx* c, const double* P, double* Q, int nrhs) {
 void launch_vector_updates(Ctx* c, int nrhs) {
   const int kp = kp_for(nrhs);
   const int grid = vec_grid(c);
-  DISPATCH_KP(kp, (k_update_xr<KP><<<grid, TB, 0, c->stream>>>(c->X.p, c->R.p, c->P.p, c->Q.p, c->dinv.p, c->Z.p, c->scal.p, nrhs, c->ndof, 1, c->partial.p)));
+  DISPATCH_KP(kp, (k_update_xr<KP><<<grid, TB, 0, c->stream>>>(c->X.p, c->R.p, c->P.p, c->Q.p, c->dinv.p, c->Z.p, c->scal.p, nrhs, c->ndof, (int64_t)0, c->partial.p)));
   DISPATCH_KP(kp, (k_update_p<KP><<<grid, TB, 0, c->stream>>>(c->P.p, c->Z.p, c->scal.p, nrhs, c->ndof)));
   c->launches += 2;
   CK(cudaGetLastError());
@@ -606,13 +606,14 @@ int solve(Ctx* c, double rtol, int maxit, int* iters, double* relres) {
   const int64_t n = c->ndof;
   const int vg = vec_grid(c), sg = spmm_grid(c);
   const int jac = (c->pkind == REMO_PRECOND_LOCAL) ? 1 : 0;
+  const int64_t tail = jac ? 0 : c->nv;  // rows >= tail: z = D^-1 r fused into the vector kernels; rows < tail: V-cycle
 
-  DISPATCH_KP(kp, (k_init<KP><<<vg, TB, 0, st>>>(c->F.p, c->constrained.p, c->dinv.p, c->X.p, c->R.p, c->Z.p, c->P.p, k, n, jac, c->partial.p)));
+  DISPATCH_KP(kp, (k_init<KP><<<vg, TB, 0, st>>>(c->F.p, c->constrained.p, c->dinv.p, c->X.p, c->R.p, c->Z.p, c->P.p, k, n, tail, c->partial.p)));
   c->launches++;
   if (!jac) {
     amg_apply(c, c->R.p, c->Z.p, k);
-    DISPATCH_KP(kp, (k_dot_rz<KP><<<vg, TB, 0, st>>>(c->R.p, c->Z.p, k, n, c->partial.p)));
-    CK(cudaMemcpyAsync(c->P.p, c->Z.p, (size_t)n * k * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    DISPATCH_KP(kp, (k_dot_rz<KP><<<vg, TB, 0, st>>>(c->R.p, c->Z.p, k, tail, c->partial.p)));
+    CK(cudaMemcpyAsync(c->P.p, c->Z.p, (size_t)tail * k * sizeof(double), cudaMemcpyDeviceToDevice, st));
     c->launches++;
   }
   k_scal_init<<<1, 1024, 0, st>>>(c->partial.p, vg, c->scal.p, c->iters_d.p, k, rtol);
@@ -638,10 +639,10 @@ int solve(Ctx* c, double rtol, int maxit, int* iters, double* relres) {
       launch_spmm(c, c->P.p, c->Q.p, k);
       if (c->prof) CK(cudaEventRecord(c->prof_ev[pe + 1], st));
       k_scal_alpha<<<1, 1024, 0, st>>>(c->partial.p, sg, c->scal.p);
-      DISPATCH_KP(kp, (k_update_xr<KP><<<vg, TB, 0, st>>>(c->X.p, c->R.p, c->P.p, c->Q.p, c->dinv.p, c->Z.p, c->scal.p, k, n, jac, c->partial.p)));
+      DISPATCH_KP(kp, (k_update_xr<KP><<<vg, TB, 0, st>>>(c->X.p, c->R.p, c->P.p, c->Q.p, c->dinv.p, c->Z.p, c->scal.p, k, n, tail, c->partial.p)));
       if (!jac) {
         amg_apply(c, c->R.p, c->Z.p, k);
-        DISPATCH_KP(kp, (k_dot_rz<KP><<<vg, TB, 0, st>>>(c->R.p, c->Z.p, k, n, c->partial.p)));
+        DISPATCH_KP(kp, (k_dot_rz<KP><<<vg, TB, 0, st>>>(c->R.p, c->Z.p, k, tail, c->partial.p)));
         c->launches++;
       }
       k_scal_beta<<<1, 1024, 0, st>>>(c->partial.p, vg, c->scal.p, c->iters_d.p);
