@@ -177,41 +177,57 @@ __global__ void k_coarse_cols(const uint64_t* __restrict__ ukeys, int64_t nnz, i
 }
 
 // ---------------------------------------------------------------- V-cycle kernels (row-major n x k blocks)
-// mode 0: OUT = X + omega * dinv * (B - A X)    (damped Jacobi sweep)      mode 1: OUT = B - A X   (residual)
-template <int G, int KP>
+// mode 0: OUT = X + omega * dinv * (B - A X)    (l1-Jacobi sweep)      mode 1: OUT = B - A X   (residual)
+// Same lane layout as the PCG SpMM (solver.cu k_spmm_p): a G-lane group owns a row, every lane owns two adjacent
+// right-hand sides (16-byte gathers; ks even) -- or one when ks == 1.
+template <int G, int KP2, int W>
 __global__ void __launch_bounds__(TB) k_smooth(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                const double* __restrict__ val, const double* __restrict__ dinv,
                                                const double* __restrict__ B, const double* __restrict__ X,
-                                               double* __restrict__ OUT, int k, int64_t n, double omega, int mode) {
-  constexpr int J = G / KP;
+                                               double* __restrict__ OUT, int ks, int64_t n, double omega, int mode) {
+  constexpr int J = G / KP2;
   constexpr int GROUPS = TB / G;
   const int lane = threadIdx.x & 31;
   const int gl = threadIdx.x % G, grp = threadIdx.x / G;
-  const int jsub = gl / KP, r = gl % KP;
-  const bool on = r < k;
-  const int rr = on ? r : 0;
+  const int jsub = gl / KP2, r2 = gl % KP2;
+  const bool on = W * r2 < ks;
+  const int cc = on ? W * r2 : 0;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((lane / G) * G));
   for (int64_t row = (int64_t)blockIdx.x * GROUPS + grp; row < n; row += (int64_t)gridDim.x * GROUPS) {
     const int64_t s = rowptr[row], e = rowptr[row + 1];
-    double acc = 0.0;
+    double acc0 = 0.0, acc1 = 0.0;
     for (int64_t base = s; base < e; base += G) {
       int32_t myc = (int32_t)row;
       double myv = 0.0;
       if (base + gl < e) { myc = col[base + gl]; myv = val[base + gl]; }
 #pragma unroll
-      for (int i = 0; i < KP; i++) {
+      for (int i = 0; i < KP2; i++) {
         const int j = i * J + jsub;
         const int32_t c = __shfl_sync(gmask, myc, j, G);
         const double v = __shfl_sync(gmask, myv, j, G);
-        acc = fma(v, X[(int64_t)c * k + rr], acc);
+        if (W == 2) {
+          const double2 x = *reinterpret_cast<const double2*>(X + (int64_t)c * ks + cc);
+          acc0 = fma(v, x.x, acc0);
+          acc1 = fma(v, x.y, acc1);
+        } else {
+          acc0 = fma(v, X[(int64_t)c * ks + cc], acc0);
+        }
       }
     }
 #pragma unroll
-    for (int o = G / 2; o >= KP; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o, G);
+    for (int o = G / 2; o >= KP2; o >>= 1) {
+      acc0 += __shfl_xor_sync(gmask, acc0, o, G);
+      if (W == 2) acc1 += __shfl_xor_sync(gmask, acc1, o, G);
+    }
     if (jsub == 0 && on) {
-      const int64_t idx = row * k + r;
-      const double res = B[idx] - acc;
-      OUT[idx] = (mode == 1) ? res : fma(omega * dinv[row], res, X[idx]);
+      const int64_t idx = row * ks + cc;
+      const double w = omega * dinv[row];
+      const double res0 = B[idx] - acc0;
+      OUT[idx] = (mode == 1) ? res0 : fma(w, res0, X[idx]);
+      if (W == 2) {
+        const double res1 = B[idx + 1] - acc1;
+        OUT[idx + 1] = (mode == 1) ? res1 : fma(w, res1, X[idx + 1]);
+      }
     }
   }
 }
@@ -292,13 +308,19 @@ __global__ void k_dense_extract(int n, const double* __restrict__ M, double* __r
   }
 }
 
+// x = Ainv b on the coarsest level: 8 lanes per output entry split the dot product, fixed-order shuffle reduction
 __global__ void k_dense_apply(int n, const double* __restrict__ Ainv, const double* __restrict__ B, double* __restrict__ X, int k) {
-  for (int e = threadIdx.x + blockIdx.x * blockDim.x; e < n * k; e += blockDim.x * gridDim.x) {
-    const int i = e / k, r = e - i * k;
-    double s = 0.0;
-    for (int j = 0; j < n; j++) s = fma(Ainv[(int64_t)i * n + j], B[(int64_t)j * k + r], s);
-    X[e] = s;
-  }
+  const int t = threadIdx.x + blockIdx.x * blockDim.x;
+  const int e = t >> 3, part = t & 7;
+  double s = 0.0;
+  const bool ok = e < n * k;
+  const int i = ok ? e / k : 0, r = ok ? e - i * k : 0;
+  if (ok)
+    for (int j = part; j < n; j += 8) s = fma(Ainv[(int64_t)i * n + j], B[(int64_t)j * k + r], s);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  if (ok && part == 0) X[e] = s;
 }
 
 int kp_of(int k) {
@@ -311,19 +333,21 @@ int kp_of(int k) {
 
 void spmm_smooth(Ctx* c, const int64_t* rowptr, const int32_t* col, const double* val, const double* dinv, const double* B,
                  const double* X, double* OUT, int k, int64_t n, double omega, int mode) {
-  const int kp = kp_of(k);
-  const int G = kp <= 8 ? 8 : kp;
-  const int64_t want = (n + (TB / G) - 1) / (TB / G);
-  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->num_sms * 8));
   cudaStream_t st = c->stream;
-  switch (kp) {
-    case 1: k_smooth<8, 1><<<grid, TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode); break;
-    case 2: k_smooth<8, 2><<<grid, TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode); break;
-    case 4: k_smooth<8, 4><<<grid, TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode); break;
-    case 8: k_smooth<8, 8><<<grid, TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode); break;
-    case 16: k_smooth<16, 16><<<grid, TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode); break;
-    default: k_smooth<32, 32><<<grid, TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode); break;
-  }
+  auto grid_of = [&](int G) {
+    const int64_t want = (n + (TB / G) - 1) / (TB / G);
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->num_sms * 8));
+  };
+  if (k & 1) {  // odd stride (only k == 1 in practice): one right-hand side per lane
+    const int kp = kp_of(k);
+    if (kp == 1) k_smooth<8, 1, 1><<<grid_of(8), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
+    else if (kp <= 8) k_smooth<8, 8, 1><<<grid_of(8), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
+    else k_smooth<32, 32, 1><<<grid_of(32), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
+  } else if (k <= 2) k_smooth<4, 1, 2><<<grid_of(4), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
+  else if (k <= 4) k_smooth<4, 2, 2><<<grid_of(4), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
+  else if (k <= 8) k_smooth<4, 4, 2><<<grid_of(4), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
+  else if (k <= 16) k_smooth<8, 8, 2><<<grid_of(8), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
+  else k_smooth<16, 16, 2><<<grid_of(16), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
   c->launches++;
   CK(cudaGetLastError());
 }
@@ -470,7 +494,7 @@ void amg_apply(Ctx* c, const double* R, double* Z, int k) {
     Ctx::AmgLevel& L = c->amg[nl - 1];
     const double* b = (nl == 1) ? R : L.b.p;
     double* x = (nl == 1) ? Z : L.x.p;
-    LAUNCH(c, k_dense_apply, grid_for(L.n * k, 128), 128, 0, (int)L.n, c->amg_dense.p, b, x, k);
+    LAUNCH(c, k_dense_apply, grid_for(L.n * k * 8, 128), 128, 0, (int)L.n, c->amg_dense.p, b, x, k);
   }
   // up
   for (int l = nl - 2; l >= 0; l--) {

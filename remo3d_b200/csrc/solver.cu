@@ -312,8 +312,19 @@ __global__ void __launch_bounds__(TB) k_update_p(double* __restrict__ P, const d
 // ---- one-block scalar kernels: finish the reductions in a fixed order (32 x 32 threads: column r, strip j)
 __device__ __forceinline__ double reduce_partials(const double* __restrict__ partial, int nblk, int stride, int slot) {
   const int r = threadIdx.x & 31, j = threadIdx.x >> 5;  // blockDim = 1024
-  double t = 0.0;
-  for (int b = j; b < nblk; b += 32) t += partial[((int64_t)b * stride + slot) * KMAX + r];
+  // four independent accumulators, loads issued 8 deep: the loop is latency bound (L2 round trips), not bandwidth bound.
+  // The summation order is fixed, so the result is still bit-reproducible.
+  double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+  int b = j;
+#pragma unroll 2
+  for (; b + 96 < nblk; b += 128) {
+    t0 += partial[((int64_t)b * stride + slot) * KMAX + r];
+    t1 += partial[((int64_t)(b + 32) * stride + slot) * KMAX + r];
+    t2 += partial[((int64_t)(b + 64) * stride + slot) * KMAX + r];
+    t3 += partial[((int64_t)(b + 96) * stride + slot) * KMAX + r];
+  }
+  for (; b < nblk; b += 32) t0 += partial[((int64_t)b * stride + slot) * KMAX + r];
+  const double t = (t0 + t1) + (t2 + t3);
   __shared__ double sh[32][33];
   __syncthreads();
   sh[j][r] = t;

@@ -210,3 +210,48 @@ def test_2d_axisymmetric_matches_oracle(ctx, order):
         for r in range(ctx.nrhs):
             u = ctx.solution(r)
             assert np.linalg.norm(u - ref["U"][:, r]) <= 1e-6 * np.linalg.norm(ref["U"][:, r])
+
+
+# ---------------------------------------------------------------------------------------------- block sizes (config C3)
+@pytest.mark.parametrize("nrhs", [1, 2, 3, 4, 7, 12, 17, 32])
+def test_block_sizes_match_oracle(ctx, nrhs):
+    """Every multi-right-hand-side width (all SpMM / vector-kernel template instances, odd widths padded to an even
+    stride) against the oracle's direct solve; sources alternate single electrodes and +1/-1 pairs."""
+    mesh, sigma, _, _ = helpers.ball_case(h_electrode=0.1, h_axis=0.4, grading=0.6)
+    flags = mesh.dirichlet_flags("dirichlet_boundary")
+    space = fo.Space(mesh.nv, mesh.elems, 2, 3)
+    A = fo.assemble(mesh.points, space, sigma, mesh.mat)
+    con = space.dirichlet_dofs(mesh.bfacets, flags)
+    axis = fo.Axis(mesh.points, space)
+    zs = axis.z[(axis.z > -8) & (axis.z < 8)]
+    rng = np.random.default_rng(nrhs)
+    ptr, sz, sf = [0], [], []
+    for r in range(nrhs):
+        if r % 3 == 2:
+            a, b = rng.choice(zs, 2, replace=False)
+            sz += [a + 1e-3, b]  # one of the pair inside an axis edge
+            sf += [1.0, -1.0]
+        else:
+            sz += [float(rng.choice(zs))]
+            sf += [1.0]
+        ptr.append(len(sz))
+    F = np.stack([fo.point_source_rhs(axis, space.ndof, sz[ptr[r]:ptr[r + 1]], sf[ptr[r]:ptr[r + 1]]) for r in range(nrhs)], axis=1)
+    U = fo.solve_direct(A, F, con)
+    ctx.mesh_set(3, mesh.points, mesh.elems, mesh.mat, mesh.bfacets, flags, mesh.axis_vertices())
+    ctx.space_build(2)
+    ctx.assemble(sigma)
+    ctx.precond_setup("multigrid" if nrhs % 2 else "local")
+    ctx.rhs_point_sources(ptr, sz, sf)
+    iters, relres = ctx.solve(rtol=1e-10, maxit=20000)
+    assert iters.shape == (nrhs,) and (relres <= 1e-10).all()
+    for r in range(nrhs):
+        np.testing.assert_allclose(ctx.rhs(r), F[:, r], rtol=0, atol=1e-15)
+        u = ctx.solution(r)
+        assert np.linalg.norm(u - U[:, r]) <= 1e-6 * np.linalg.norm(U[:, r]), r
+    pts = rng.choice(zs, 6)
+    rhs = rng.integers(0, nrhs, 6)
+    got = ctx.sample_axis(pts, rhs)
+    want = np.array([fo.sample_axis(axis, U[:, r], z) for z, r in zip(pts, rhs)])
+    np.testing.assert_allclose(got, want, rtol=1e-6)
+    with pytest.raises(_cabi.RemoError):
+        ctx.solution(nrhs)  # the padding column of an odd width is not addressable
