@@ -465,17 +465,22 @@ void amg_setup(Ctx* c) {
   }
 }
 
+// work blocks of every level for k right-hand sides (grow-only; must be called before a CUDA-graph capture of amg_apply)
+void amg_prepare(Ctx* c, int k) {
+  for (int l = 0; l < c->amg_nlev; l++) {
+    Ctx::AmgLevel& L = c->amg[l];
+    L.b.ensure(L.n * k, c->stream); L.x.ensure(L.n * k, c->stream); L.t.ensure(L.n * k, c->stream);
+  }
+  c->amg_nrhs = k;
+}
+
 // z_vert = V-cycle(r_vert) on the leading nv rows of the ndof x k blocks R, Z of the PCG.
 void amg_apply(Ctx* c, const double* R, double* Z, int k) {
   cudaStream_t st = c->stream;
   const double alpha = c->amg_alpha;
   const int sweeps = c->amg_sweeps;
   const int nl = c->amg_nlev;
-  for (int l = 0; l < nl; l++) {  // grow-only: a no-op once the buffers are large enough
-    Ctx::AmgLevel& L = c->amg[l];
-    L.b.ensure(L.n * k, st); L.x.ensure(L.n * k, st); L.t.ensure(L.n * k, st);
-  }
-  c->amg_nrhs = k;
+  amg_prepare(c, k);
   // down
   for (int l = 0; l < nl - 1; l++) {
     Ctx::AmgLevel& L = c->amg[l];

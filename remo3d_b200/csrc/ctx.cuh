@@ -135,6 +135,7 @@ struct Ctx {
   bool have_rhs = false, have_solution = false;
 
   // ---- per-launch SpMM timing inside remo_solve (remo_profile): CUDA events around every SpMM launch
+  bool use_graph = true;  // replay one PCG iteration as a CUDA graph (off while profiling: events cannot sit inside a graph)
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev;
   double prof_spmm_ms = 0.0;
@@ -197,6 +198,7 @@ void alloc_solver_state(Ctx* c, int nrhs);
 // amg.cu
 void amg_setup(Ctx* c);
 void amg_apply(Ctx* c, const double* R, double* Z, int nrhs);
+void amg_prepare(Ctx* c, int nrhs);
 void amg_release(Ctx* c);
 void spmm_smooth(Ctx* c, const int64_t* rowptr, const int32_t* col, const double* val, const double* dinv, const double* B,
                  const double* X, double* OUT, int k, int64_t n, double omega, int mode);

@@ -635,30 +635,62 @@ int solve(Ctx* c, double rtol, int maxit, int* iters, double* relres) {
   std::vector<double> hs(S_NSLOT * KMAX);
   int it = 0;
   bool done = false;
+
+  // one PCG iteration = ~8 (Jacobi) to ~40 (multigrid) launches, most of them tiny: the launch-bound inner loop is
+  // captured once per solve as a CUDA graph and replayed; the host only polls the convergence flags every 16 iterations
+  auto iteration = [&](int itno) {
+    const size_t pe = (size_t)2 * itno;
+    if (c->prof) {
+      while (c->prof_ev.size() < pe + 2) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        c->prof_ev.push_back(e);
+      }
+      CK(cudaEventRecord(c->prof_ev[pe], st));
+    }
+    launch_spmm(c, c->P.p, c->Q.p, k);
+    if (c->prof) CK(cudaEventRecord(c->prof_ev[pe + 1], st));
+    k_scal_alpha<<<1, 1024, 0, st>>>(c->partial.p, sg, c->scal.p);
+    DISPATCH_KP(kp, (k_update_xr<KP><<<vg, TB, 0, st>>>(c->X.p, c->R.p, c->P.p, c->Q.p, c->dinv.p, c->Z.p, c->scal.p, k, n, tail, c->partial.p)));
+    if (!jac) {
+      amg_apply(c, c->R.p, c->Z.p, k);
+      DISPATCH_KP(kp, (k_dot_rz<KP><<<vg, TB, 0, st>>>(c->R.p, c->Z.p, k, tail, c->partial.p)));
+      c->launches++;
+    }
+    k_scal_beta<<<1, 1024, 0, st>>>(c->partial.p, vg, c->scal.p, c->iters_d.p);
+    DISPATCH_KP(kp, (k_update_p<KP><<<vg, TB, 0, st>>>(c->P.p, c->Z.p, c->scal.p, k, n)));
+    c->launches += 4;
+  };
+
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  int64_t launches_per_iter = 0;
+  const bool graphs = c->use_graph && !c->prof && getenv("REMO_NO_GRAPH") == nullptr;
+  if (graphs) {
+    if (!jac) amg_prepare(c, k);  // no allocation may happen inside the capture
+    const int64_t l0 = c->launches;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    try {
+      iteration(0);
+    } catch (...) {
+      cudaStreamEndCapture(st, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    CK(cudaStreamEndCapture(st, &graph));
+    launches_per_iter = c->launches - l0;
+    c->launches = l0;
+    CK(cudaGraphInstantiate(&gexec, graph, 0));
+  }
   while (it < maxit && !done) {
     const int chunk = std::min(check_every, maxit - it);
     for (int q = 0; q < chunk; q++) {
-      const size_t pe = (size_t)2 * (it + q);
-      if (c->prof) {
-        while (c->prof_ev.size() < pe + 2) {
-          cudaEvent_t e;
-          CK(cudaEventCreate(&e));
-          c->prof_ev.push_back(e);
-        }
-        CK(cudaEventRecord(c->prof_ev[pe], st));
+      if (graphs) {
+        CK(cudaGraphLaunch(gexec, st));
+        c->launches += launches_per_iter;
+      } else {
+        iteration(it + q);
       }
-      launch_spmm(c, c->P.p, c->Q.p, k);
-      if (c->prof) CK(cudaEventRecord(c->prof_ev[pe + 1], st));
-      k_scal_alpha<<<1, 1024, 0, st>>>(c->partial.p, sg, c->scal.p);
-      DISPATCH_KP(kp, (k_update_xr<KP><<<vg, TB, 0, st>>>(c->X.p, c->R.p, c->P.p, c->Q.p, c->dinv.p, c->Z.p, c->scal.p, k, n, tail, c->partial.p)));
-      if (!jac) {
-        amg_apply(c, c->R.p, c->Z.p, k);
-        DISPATCH_KP(kp, (k_dot_rz<KP><<<vg, TB, 0, st>>>(c->R.p, c->Z.p, k, tail, c->partial.p)));
-        c->launches++;
-      }
-      k_scal_beta<<<1, 1024, 0, st>>>(c->partial.p, vg, c->scal.p, c->iters_d.p);
-      DISPATCH_KP(kp, (k_update_p<KP><<<vg, TB, 0, st>>>(c->P.p, c->Z.p, c->scal.p, k, n)));
-      c->launches += 4;
     }
     CK(cudaGetLastError());
     it += chunk;
@@ -668,6 +700,8 @@ int solve(Ctx* c, double rtol, int maxit, int* iters, double* relres) {
     for (int r = 0; r < k; r++)
       if (hs[S_ACTIVE * KMAX + r] != 0.0) done = false;
   }
+  if (gexec) cudaGraphExecDestroy(gexec);
+  if (graph) cudaGraphDestroy(graph);
   std::vector<int> hit(KMAX);
   CK(cudaMemcpyAsync(hit.data(), c->iters_d.p, KMAX * sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
