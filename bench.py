@@ -219,6 +219,13 @@ def run_b200(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         per_launch = spmm_ms / max(spmm_n, 1) / 1e3
+        traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per SpMM launch from the committed ncu --set full capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_spmm_traffic_%s.json" % args.size)))
+            if tj.get("order") == args.order and tj.get("nrhs") == nrhs:
+                traffic = tj["traffic_bytes_per_launch"]
+        except Exception:
+            pass
         achieved = spmm_bytes(nnz, ndof, nrhs) / per_launch / 1e9 if spmm_n else 0.0
         h2d = sum(host[k].numel() * host[k].element_size() for k in names) + flat["src_z"].nbytes * 2 + flat["src_ptr"].nbytes \
             + flat["pt_rhs"].nbytes + 3 * flat["pt_z0"].nbytes + len(SIGMA) * 8
@@ -240,7 +247,7 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_spmm (PCG SpMM + fused p.q)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "bytes_per_launch": spmm_bytes(nnz, ndof, nrhs), "avg_launch_ms": per_launch * 1e3, "launches_timed": int(spmm_n),
                          "frac_of_8TBs_spec": achieved / 8000.0, "spmm_share_of_step": spmm_ms / ms_prof,
                          "timed_with": "CUDA events around every SpMM launch in %d extra steps run right after the timed regions (plain launches instead of the CUDA graph)" % args.steps},

@@ -7,14 +7,19 @@ reference hard-codes: `order` (3, ngsolve_functions.py:27), `rtol` (CG tolerance
 Plotting (`save_results` figures) is out of scope; the text writer keeps the reference's file format.
 """
 import datetime
+import multiprocessing
 import os
 import queue
 import threading
-from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
 from . import _cabi, model_io, model_mesh, planner, tools as tl, worker
+
+
+def _build_mesh_job(args):
+    """Runs in a mesh-pool process: one task's mesh + sigma list (pure host work)."""
+    return model_mesh.build_task_mesh(*args)
 
 
 class Model:
@@ -31,6 +36,7 @@ class Model:
         self.logs = None
         self.task_records = None
         self._contexts = None
+        self._mesh_pool = None
 
     @classmethod
     def compute_synthetic_logs(cls, tools, measurement_depths, formation_model, borehole_model,
@@ -105,12 +111,24 @@ class Model:
             raise ValueError("Minimal number of gpu workers is 0")
         self.cpu_workers = cpu_workers
         self.gpu_workers = max(1, gpu_workers)
-        self._contexts = [_cabi.Context(d) for d in range(self.gpu_workers)]  # fails loudly without a B200
+        # host mesh-generation pool: worker PROCESSES (mesh generation is Python/NumPy/Qhull and would serialise on the GIL
+        # in threads), forked before any CUDA context exists in this process; they never touch the GPU
+        self._mesh_pool = multiprocessing.get_context("fork").Pool(cpu_workers)
+        try:
+            self._contexts = [_cabi.Context(d) for d in range(self.gpu_workers)]  # fails loudly without a B200
+        except Exception:
+            self._mesh_pool.terminate()
+            self._mesh_pool = None
+            raise
 
     def shutdown_workers(self):
         for c in self._contexts or []:
             c.close()
         self._contexts = None
+        if getattr(self, "_mesh_pool", None) is not None:
+            self._mesh_pool.close()
+            self._mesh_pool.join()
+            self._mesh_pool = None
 
     # ---- simulation (remo3d.py:723-884)
     def simulate_logs(self, measurement_depths, domain_radius=50, batch_size=5, mesh_generator="auto", preconditioner="multigrid",
@@ -144,11 +162,8 @@ class Model:
         mud_resistivities = np.interp(simulation_depths, borehole_model[:, 0], borehole_model[:, 2])
         print("{} simulation tasks prepared".format(n_tasks))
 
-        def make_job(i):
-            task = task_list[i]
-            mesh, sigma = model_mesh.build_task_mesh(self.formation_model, borehole_geometry, self.dip_rad, simulation_depths[task[0]],
-                                                     task[1][0], mud_resistivities[task[0]], domain_radius, mesh_options)
-            return i, task, mesh, sigma
+        job_args = [(self.formation_model, borehole_geometry, self.dip_rad, simulation_depths[t[0]], t[1][0], mud_resistivities[t[0]],
+                     domain_radius, mesh_options) for t in task_list]
 
         jobs = queue.Queue(maxsize=2 * len(self._contexts) + 2)
         triples, records, lock = [], [None] * n_tasks, threading.Lock()
@@ -168,9 +183,9 @@ class Model:
         threads = [threading.Thread(target=gpu_loop, args=(c,), daemon=True) for c in self._contexts]
         for th in threads:
             th.start()
-        with ThreadPoolExecutor(max_workers=self.cpu_workers) as pool:
-            for job in pool.map(make_job, range(n_tasks)):  # meshes are produced ahead, in task order
-                jobs.put(job)
+        # meshes are produced ahead by the process pool, in task order, while the GPU workers solve
+        for i, (mesh, sigma) in enumerate(self._mesh_pool.imap(_build_mesh_job, job_args, chunksize=1)):
+            jobs.put((i, task_list[i], mesh, sigma))
         for _ in threads:
             jobs.put(None)
         for th in threads:
