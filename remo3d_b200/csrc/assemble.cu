@@ -235,6 +235,7 @@ void assemble(Ctx* c, int nmat, const double* sigma) {
   CK(cudaMemcpyAsync(c->sigma.p, sigma, nmat * sizeof(double), cudaMemcpyDefault, c->stream));
   assemble_kernels_only(c);
   c->have_matrix = true;
+  c->have_sell = false;
   c->pkind = -1;
   c->have_solution = false;
 }

@@ -135,7 +135,7 @@ int remo_mesh_set(void* vctx, int dim, int64_t nv, const double* xyz, int64_t nt
     if (naxis < 0 || (naxis > 0 && !axis_vertices)) FAIL(REMO_ERR_ARG, "remo_mesh_set: axis array missing");
     StageTimer timer(c, ST_MESH);
     cudaStream_t st = c->stream;
-    c->have_mesh = c->have_space = c->have_matrix = c->have_rhs = c->have_solution = false;
+    c->have_mesh = c->have_space = c->have_matrix = c->have_sell = c->have_rhs = c->have_solution = false;
     c->pkind = -1;
     c->dim = dim; c->nv = nv; c->nt = nt; c->nb = nb; c->naxis = naxis;
     c->xyz.ensure(nv * dim, st); c->elems.ensure(nt * (dim + 1), st); c->mat.ensure(nt, st);
@@ -293,7 +293,7 @@ int remo_kernel_time(void* vctx, int which, int nrhs, int reps, float* ms) {
       }
       if (c->pkind < 0) precond_setup(c, REMO_PRECOND_LOCAL);
       // deterministic non-trivial vectors: P = dinv-scaled ones pattern is not needed for timing; reuse F
-      CK(cudaMemcpyAsync(c->P.p, c->F.p, (size_t)c->ndof * c->nrhs * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpy2DAsync(c->P.p, (size_t)c->pstride * sizeof(double), c->F.p, (size_t)c->nrhs * sizeof(double), (size_t)c->nrhs * sizeof(double), (size_t)c->ndof, cudaMemcpyDeviceToDevice, st));
       CK(cudaMemsetAsync(c->scal.p, 0, c->scal.n * sizeof(double), st));
     }
     cudaEvent_t a, b;

@@ -97,6 +97,17 @@ struct Ctx {
   DBuf<int32_t> col;          // nnz, ascending per row
   DBuf<double> val;           // nnz
   bool have_space = false, have_matrix = false;
+  // sliced-ELLPACK copy of the matrix for the multi-RHS PCG SpMM (sell.cu): slices of 8 rows, chunks of 4 entries
+  DBuf<int64_t> sell_ptr;   // nslices+1: first chunk of every slice
+  DBuf<int32_t> sell_col;   // chunks x 8 rows x 4
+  DBuf<double> sell_val;    // chunks x 8 rows x 4
+  DBuf<int32_t> sell_row;   // row slot -> matrix row (sorted by length inside windows), -1 = padding
+  DBuf<int64_t> sell_part;  // blocked distribution: first slice of every CTA (equal chunk counts)
+  int sell_nparts = 0;
+  DBuf<int64_t> sell_wpart;  // streaming kernel: first slice of every warp
+  int sell_sgrid = 0;
+  int64_t sell_chunks = 0, sell_slots = 0;
+  bool have_sell = false;
 
   // ---- numeric
   DBuf<double> gm;     // nt x npair: sigma |K| grad l_i . grad l_j
@@ -128,6 +139,7 @@ struct Ctx {
   // ---- right-hand sides / PCG state, row-major ndof x nrhs
   int nrhs = 0;       // internal column count = row stride of the vector blocks (user count rounded up to even)
   int nrhs_user = 0;  // right-hand sides the caller asked for
+  int pstride = 0;    // row stride of the P block alone: = nrhs, or the next power of two when the SELL SpMM gathers it
   DBuf<double> F, X, R, Z, P, Q;
   DBuf<double> partial;  // per-block partial dot products
   DBuf<double> scal;     // device scalars, see solver.cu
@@ -195,6 +207,12 @@ void apparent_resistivity(Ctx* c, int npts, const int32_t* pt_rhs, const double*
 void launch_spmm(Ctx* c, const double* P, double* Q, int nrhs);
 void launch_vector_updates(Ctx* c, int nrhs);
 void alloc_solver_state(Ctx* c, int nrhs);
+int spmm_variant();
+// sell.cu
+int sell_pstride(int ks);
+void sell_build(Ctx* c);
+int sell_grid(const Ctx* c);
+void launch_spmm_sell(Ctx* c, const double* P, double* Q, int ks, int pstride);
 // amg.cu
 void amg_setup(Ctx* c);
 void amg_apply(Ctx* c, const double* R, double* Z, int nrhs);

@@ -227,8 +227,8 @@ __device__ __forceinline__ void block_partials(double a, double b, double* __res
 template <int KP>
 __global__ void __launch_bounds__(TB) k_init(const double* __restrict__ F, const uint8_t* __restrict__ constrained,
                                              const double* __restrict__ dinv, double* __restrict__ X, double* __restrict__ R,
-                                             double* __restrict__ Z, double* __restrict__ P, int k, int64_t n, int64_t tail_from,
-                                             double* __restrict__ partial) {
+                                             double* __restrict__ Z, double* __restrict__ P, int k, int kps, int64_t n,
+                                             int64_t tail_from, double* __restrict__ partial) {
   const int r = threadIdx.x % KP, g = threadIdx.x / KP;
   constexpr int G = TB / KP;
   double rr = 0.0, rz = 0.0;
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(TB) k_init(const double* __restrict__ F, const
       if (i >= tail_from) {  // rows preconditioned by their diagonal: all rows ("local"), the high-order rows ("multigrid")
         const double z = dinv[i] * f;
         Z[idx] = z;
-        P[idx] = z;
+        P[i * kps + r] = z;
         rz = fma(f, z, rz);
       }
     }
@@ -253,8 +253,8 @@ __global__ void __launch_bounds__(TB) k_init(const double* __restrict__ F, const
 template <int KP>
 __global__ void __launch_bounds__(TB) k_update_xr(double* __restrict__ X, double* __restrict__ R, const double* __restrict__ P,
                                                   const double* __restrict__ Q, const double* __restrict__ dinv,
-                                                  double* __restrict__ Z, const double* __restrict__ scal, int k, int64_t n,
-                                                  int64_t tail_from, double* __restrict__ partial) {
+                                                  double* __restrict__ Z, const double* __restrict__ scal, int k, int kps,
+                                                  int64_t n, int64_t tail_from, double* __restrict__ partial) {
   const int r = threadIdx.x % KP, g = threadIdx.x / KP;
   constexpr int G = TB / KP;
   double rr = 0.0, rz = 0.0;
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(TB) k_update_xr(double* __restrict__ X, double
     const double alpha = scal[S_ALPHA * KMAX + r];
     for (int64_t i = (int64_t)blockIdx.x * G + g; i < n; i += (int64_t)gridDim.x * G) {
       const int64_t idx = i * k + r;
-      X[idx] = fma(alpha, P[idx], X[idx]);
+      X[idx] = fma(alpha, P[i * kps + r], X[idx]);
       const double res = fma(-alpha, Q[idx], R[idx]);
       R[idx] = res;
       rr = fma(res, res, rr);
@@ -298,14 +298,14 @@ __global__ void __launch_bounds__(TB) k_dot_rz(const double* __restrict__ R, con
 // p = z + beta p
 template <int KP>
 __global__ void __launch_bounds__(TB) k_update_p(double* __restrict__ P, const double* __restrict__ Z,
-                                                 const double* __restrict__ scal, int k, int64_t n) {
+                                                 const double* __restrict__ scal, int k, int kps, int64_t n) {
   const int r = threadIdx.x % KP, g = threadIdx.x / KP;
   constexpr int G = TB / KP;
   if (r >= k) return;
   const double beta = scal[S_BETA * KMAX + r];
   for (int64_t i = (int64_t)blockIdx.x * G + g; i < n; i += (int64_t)gridDim.x * G) {
-    const int64_t idx = i * k + r;
-    P[idx] = fma(beta, P[idx], Z[idx]);
+    const int64_t ip = i * kps + r;
+    P[ip] = fma(beta, P[ip], Z[i * k + r]);
   }
 }
 
@@ -481,7 +481,8 @@ int kp_for(int k) {
   }
 
 int vec_grid(Ctx* c) { return c->num_sms * 8; }
-int spmm_grid(Ctx* c) { return c->num_sms * 8; }
+bool use_sell(const Ctx* c, int nrhs, const double* P) { return c->have_sell && c->pstride >= 2 && (nrhs & 1) == 0 && P == c->P.p; }
+int spmm_grid(Ctx* c, int nrhs) { return use_sell(c, nrhs, c->P.p) ? sell_grid(c) : c->num_sms * 8; }
 
 void check_bad(Ctx* c, DBuf<int>& bad, const char* who) {
   int h = 0;
@@ -499,26 +500,35 @@ void alloc_solver_state(Ctx* c, int nrhs) {
   cudaStream_t st = c->stream;
   const size_t n = (size_t)c->ndof * nrhs;
   c->F.ensure(n, st); c->X.ensure(n, st); c->R.ensure(n, st);
-  c->Z.ensure(n, st); c->P.ensure(n, st); c->Q.ensure(n, st);
-  c->partial.ensure((size_t)std::max(vec_grid(c), spmm_grid(c)) * 2 * KMAX, st);
+  c->Z.ensure(n, st); c->Q.ensure(n, st);
+  // P alone gets a power-of-two row stride when the SELL SpMM gathers it (sell.cu): no gathered row straddles a line
+  c->pstride = (spmm_variant() >= 5 && nrhs >= 2 && (nrhs & 1) == 0) ? sell_pstride(nrhs) : nrhs;
+  c->P.ensure((size_t)c->ndof * c->pstride, st);
+  if (c->pstride != nrhs) CK(cudaMemsetAsync(c->P.p, 0, (size_t)c->ndof * c->pstride * sizeof(double), st));
+  c->partial.ensure((size_t)std::max(vec_grid(c), c->num_sms * 64) * 2 * KMAX, st);  // room for any SpMM grid (sell.cu caps its own)
   CK(cudaMemsetAsync(c->partial.p, 0, c->partial.n * sizeof(double), st));
   c->scal.ensure(S_NSLOT * KMAX, st);
   c->iters_d.ensure(KMAX, st);
   c->nrhs = nrhs;
 }
 
-static int spmm_variant() {
+int spmm_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("REMO_SPMM_VARIANT");
-    v = e ? atoi(e) : 4;
+    v = e ? atoi(e) : 5;
   }
   return v;
 }
 
 void launch_spmm(Ctx* c, const double* P, double* Q, int nrhs) {
   const int kp = kp_for(nrhs);
-  const int grid = spmm_grid(c);
+  const int grid = c->num_sms * 8;
+  if (use_sell(c, nrhs, P)) {  // SELL copy + power-of-two P stride (sell.cu)
+    launch_spmm_sell(c, P, Q, nrhs, c->pstride);
+    return;
+  }
+  if (c->pstride != nrhs && P == c->P.p) FAIL(REMO_ERR_STATE, "launch_spmm: P has stride %d but no SELL matrix exists", c->pstride);
   if (spmm_variant() >= 3 && (nrhs & 1) == 0) {  // even stride: paired-column kernel
     auto* rp = c->rowptr.p; auto* cl = c->col.p; auto* vl = c->val.p; auto* cs = c->constrained.p;
     double* pt = c->partial.p;
@@ -558,8 +568,8 @@ void launch_spmm(Ctx* c, const double* P, double* Q, int nrhs) {
 void launch_vector_updates(Ctx* c, int nrhs) {
   const int kp = kp_for(nrhs);
   const int grid = vec_grid(c);
-  DISPATCH_KP(kp, (k_update_xr<KP><<<grid, TB, 0, c->stream>>>(c->X.p, c->R.p, c->P.p, c->Q.p, c->dinv.p, c->Z.p, c->scal.p, nrhs, c->ndof, (int64_t)0, c->partial.p)));
-  DISPATCH_KP(kp, (k_update_p<KP><<<grid, TB, 0, c->stream>>>(c->P.p, c->Z.p, c->scal.p, nrhs, c->ndof)));
+  DISPATCH_KP(kp, (k_update_xr<KP><<<grid, TB, 0, c->stream>>>(c->X.p, c->R.p, c->P.p, c->Q.p, c->dinv.p, c->Z.p, c->scal.p, nrhs, c->pstride, c->ndof, (int64_t)0, c->partial.p)));
+  DISPATCH_KP(kp, (k_update_p<KP><<<grid, TB, 0, c->stream>>>(c->P.p, c->Z.p, c->scal.p, nrhs, c->pstride, c->ndof)));
   c->launches += 2;
   CK(cudaGetLastError());
 }
@@ -571,6 +581,7 @@ void precond_setup(Ctx* c, int kind) {
   c->dinv.ensure(c->ndof, c->stream);
   LAUNCH(c, k_dinv, grid_for(c->ndof, TB), TB, 0, c->rowptr.p, c->col.p, c->val.p, c->constrained.p, c->dinv.p, c->ndof);
   if (kind == REMO_PRECOND_MULTIGRID) amg_setup(c);
+  if (spmm_variant() >= 5 && !c->have_sell) sell_build(c);
   c->pkind = kind;
 }
 
@@ -615,16 +626,17 @@ int solve(Ctx* c, double rtol, int maxit, int* iters, double* relres) {
   cudaStream_t st = c->stream;
   const int k = c->nrhs, kp = kp_for(k);
   const int64_t n = c->ndof;
-  const int vg = vec_grid(c), sg = spmm_grid(c);
+  const int vg = vec_grid(c), sg = spmm_grid(c, k);
   const int jac = (c->pkind == REMO_PRECOND_LOCAL) ? 1 : 0;
   const int64_t tail = jac ? 0 : c->nv;  // rows >= tail: z = D^-1 r fused into the vector kernels; rows < tail: V-cycle
 
-  DISPATCH_KP(kp, (k_init<KP><<<vg, TB, 0, st>>>(c->F.p, c->constrained.p, c->dinv.p, c->X.p, c->R.p, c->Z.p, c->P.p, k, n, tail, c->partial.p)));
+  const int kps = c->pstride;
+  DISPATCH_KP(kp, (k_init<KP><<<vg, TB, 0, st>>>(c->F.p, c->constrained.p, c->dinv.p, c->X.p, c->R.p, c->Z.p, c->P.p, k, kps, n, tail, c->partial.p)));
   c->launches++;
   if (!jac) {
     amg_apply(c, c->R.p, c->Z.p, k);
     DISPATCH_KP(kp, (k_dot_rz<KP><<<vg, TB, 0, st>>>(c->R.p, c->Z.p, k, tail, c->partial.p)));
-    CK(cudaMemcpyAsync(c->P.p, c->Z.p, (size_t)tail * k * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpy2DAsync(c->P.p, (size_t)kps * sizeof(double), c->Z.p, (size_t)k * sizeof(double), (size_t)k * sizeof(double), (size_t)tail, cudaMemcpyDeviceToDevice, st));
     c->launches++;
   }
   k_scal_init<<<1, 1024, 0, st>>>(c->partial.p, vg, c->scal.p, c->iters_d.p, k, rtol);
@@ -651,14 +663,14 @@ int solve(Ctx* c, double rtol, int maxit, int* iters, double* relres) {
     launch_spmm(c, c->P.p, c->Q.p, k);
     if (c->prof) CK(cudaEventRecord(c->prof_ev[pe + 1], st));
     k_scal_alpha<<<1, 1024, 0, st>>>(c->partial.p, sg, c->scal.p);
-    DISPATCH_KP(kp, (k_update_xr<KP><<<vg, TB, 0, st>>>(c->X.p, c->R.p, c->P.p, c->Q.p, c->dinv.p, c->Z.p, c->scal.p, k, n, tail, c->partial.p)));
+    DISPATCH_KP(kp, (k_update_xr<KP><<<vg, TB, 0, st>>>(c->X.p, c->R.p, c->P.p, c->Q.p, c->dinv.p, c->Z.p, c->scal.p, k, kps, n, tail, c->partial.p)));
     if (!jac) {
       amg_apply(c, c->R.p, c->Z.p, k);
       DISPATCH_KP(kp, (k_dot_rz<KP><<<vg, TB, 0, st>>>(c->R.p, c->Z.p, k, tail, c->partial.p)));
       c->launches++;
     }
     k_scal_beta<<<1, 1024, 0, st>>>(c->partial.p, vg, c->scal.p, c->iters_d.p);
-    DISPATCH_KP(kp, (k_update_p<KP><<<vg, TB, 0, st>>>(c->P.p, c->Z.p, c->scal.p, k, n)));
+    DISPATCH_KP(kp, (k_update_p<KP><<<vg, TB, 0, st>>>(c->P.p, c->Z.p, c->scal.p, k, kps, n)));
     c->launches += 4;
   };
 

@@ -6,7 +6,7 @@ import bench
 from remo3d_b200 import _cabi
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--size", default="1M")
+ap.add_argument("--size", default=os.environ.get("REMO_PROBE_SIZE", "1M"))
 ap.add_argument("--order", type=int, default=2)
 ap.add_argument("--ks", default="1,5,8")
 ap.add_argument("--reps", type=int, default=20)
