@@ -97,29 +97,6 @@ __device__ __forceinline__ uint64_t spread21(uint64_t v) {
   return v;
 }
 
-__global__ void k_bbox(const double* __restrict__ xyz, int64_t nv, int dim, double* __restrict__ lohi) {
-  // one block; lohi[0..2] = min, [3..5] = max
-  __shared__ double smin[3][TB], smax[3][TB];
-  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
-  for (int64_t i = threadIdx.x; i < nv; i += blockDim.x)
-    for (int d = 0; d < dim; d++) {
-      const double v = xyz[i * dim + d];
-      mn[d] = fmin(mn[d], v);
-      mx[d] = fmax(mx[d], v);
-    }
-  for (int d = 0; d < 3; d++) { smin[d][threadIdx.x] = mn[d]; smax[d][threadIdx.x] = mx[d]; }
-  __syncthreads();
-  for (int s = TB / 2; s > 0; s >>= 1) {
-    if (threadIdx.x < s)
-      for (int d = 0; d < 3; d++) {
-        smin[d][threadIdx.x] = fmin(smin[d][threadIdx.x], smin[d][threadIdx.x + s]);
-        smax[d][threadIdx.x] = fmax(smax[d][threadIdx.x], smax[d][threadIdx.x + s]);
-      }
-    __syncthreads();
-  }
-  if (threadIdx.x < 3) { lohi[threadIdx.x] = smin[threadIdx.x][0]; lohi[3 + threadIdx.x] = smax[threadIdx.x][0]; }
-}
-
 __global__ void k_morton(const double* __restrict__ xyz, int64_t nv, int dim, const double* __restrict__ lohi,
                          uint64_t* __restrict__ code, uint32_t* __restrict__ idx) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -392,12 +369,11 @@ void amg_setup(Ctx* c) {
     LAUNCH(c, k_vv_fill, grid_for(nv, TB), TB, 0, c->rowptr.p, c->col.p, c->val.p, c->constrained.p, nv, L.rowptr.p, L.col.p, L.val.p);
     LAUNCH(c, k_level_dinv, grid_for(nv, TB), TB, 0, L.rowptr.p, L.col.p, L.val.p, c->constrained.p, nv, L.dinv.p);
     // ---- aggregates of level 0 from the Morton ranks of the vertex coordinates
-    double* lohi = scratch<double>(c, 9, 8);
+    const double* lohi = mesh_bbox(c);
     uint64_t* code = scratch<uint64_t>(c, 0, nv);
     uint64_t* codes = scratch<uint64_t>(c, 1, nv);
     uint32_t* idx = scratch<uint32_t>(c, 2, nv);
     uint32_t* perm = scratch<uint32_t>(c, 3, nv);
-    LAUNCH(c, k_bbox, 1, TB, 0, c->xyz.p, nv, c->dim, lohi);
     LAUNCH(c, k_morton, grid_for(nv, TB), TB, 0, c->xyz.p, nv, c->dim, lohi, code, idx);
     CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, code, codes, idx, perm, nv, 0, 63, st));
     c->tmp.ensure(bytes, st);

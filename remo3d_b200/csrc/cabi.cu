@@ -135,7 +135,7 @@ int remo_mesh_set(void* vctx, int dim, int64_t nv, const double* xyz, int64_t nt
     if (naxis < 0 || (naxis > 0 && !axis_vertices)) FAIL(REMO_ERR_ARG, "remo_mesh_set: axis array missing");
     StageTimer timer(c, ST_MESH);
     cudaStream_t st = c->stream;
-    c->have_mesh = c->have_space = c->have_matrix = c->have_sell = c->have_rhs = c->have_solution = false;
+    c->have_mesh = c->have_bbox = c->have_space = c->have_matrix = c->have_sell = c->have_rhs = c->have_solution = false;
     c->pkind = -1;
     c->dim = dim; c->nv = nv; c->nt = nt; c->nb = nb; c->naxis = naxis;
     c->xyz.ensure(nv * dim, st); c->elems.ensure(nt * (dim + 1), st); c->mat.ensure(nt, st);

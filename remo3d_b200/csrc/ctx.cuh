@@ -80,6 +80,8 @@ struct Ctx {
   DBuf<int32_t> axis_v;   // naxis
   DBuf<double> axis_z;    // naxis
   bool have_mesh = false;
+  DBuf<double> bbox;  // [0..5] = min / max of the vertex coordinates (mesh_bbox), then per-block scratch
+  bool have_bbox = false;
 
   // ---- space (remo_space_build)
   int order = 0, nld = 0, nle = 0, nlf = 0, npair = 0;
@@ -209,6 +211,7 @@ void launch_vector_updates(Ctx* c, int nrhs);
 void alloc_solver_state(Ctx* c, int nrhs);
 int spmm_variant();
 // sell.cu
+const double* mesh_bbox(Ctx* c);
 int sell_pstride(int ks);
 void sell_build(Ctx* c);
 int sell_grid(const Ctx* c);

@@ -65,14 +65,17 @@ __device__ __forceinline__ uint64_t spread21s(uint64_t v) {
   return v;
 }
 
-__global__ void k_sell_bbox(const double* __restrict__ xyz, int64_t nv, int dim, double* __restrict__ lohi) {
+// bounding box of the vertices, two stages: per-block min / max, then one block over the block results
+__global__ void k_bbox_stage(const double* __restrict__ in, int64_t count, int dim, int from_blocks, double* __restrict__ out) {
+  // from_blocks == 0: `in` = xyz (count vertices);  1: `in` = count block results [6] -> out[0..2] = min, out[3..5] = max
   __shared__ double smin[3][TB], smax[3][TB];
   double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
-  for (int64_t i = threadIdx.x; i < nv; i += blockDim.x)
+  for (int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x; i < count; i += (int64_t)gridDim.x * TB)
     for (int d = 0; d < dim; d++) {
-      const double v = xyz[i * dim + d];
-      mn[d] = fmin(mn[d], v);
-      mx[d] = fmax(mx[d], v);
+      const double lo = from_blocks ? in[i * 6 + d] : in[i * dim + d];
+      const double hi = from_blocks ? in[i * 6 + 3 + d] : lo;
+      mn[d] = fmin(mn[d], lo);
+      mx[d] = fmax(mx[d], hi);
     }
   for (int d = 0; d < 3; d++) { smin[d][threadIdx.x] = mn[d]; smax[d][threadIdx.x] = mx[d]; }
   __syncthreads();
@@ -84,7 +87,10 @@ __global__ void k_sell_bbox(const double* __restrict__ xyz, int64_t nv, int dim,
       }
     __syncthreads();
   }
-  if (threadIdx.x < 3) { lohi[threadIdx.x] = smin[threadIdx.x][0]; lohi[3 + threadIdx.x] = smax[threadIdx.x][0]; }
+  if (threadIdx.x < 3) {
+    out[(int64_t)blockIdx.x * 6 + threadIdx.x] = smin[threadIdx.x][0];
+    out[(int64_t)blockIdx.x * 6 + 3 + threadIdx.x] = smax[threadIdx.x][0];
+  }
 }
 
 __global__ void k_sell_morton(SpaceView s, const double* __restrict__ xyz, const double* __restrict__ lohi, int classes,
@@ -366,6 +372,18 @@ __global__ void __launch_bounds__(256, MINB) k_spmm_stream8(const int64_t* __res
 
 }  // namespace
 
+// min (lohi[0..2]) and max (lohi[3..5]) of the vertex coordinates, computed once per mesh
+const double* mesh_bbox(Ctx* c) {
+  if (!c->have_bbox) {
+    const int nb = c->num_sms * 4;
+    c->bbox.ensure((size_t)(nb + 1) * 6, c->stream);
+    LAUNCH(c, k_bbox_stage, nb, TB, 0, c->xyz.p, c->nv, c->dim, 0, c->bbox.p + 6);
+    LAUNCH(c, k_bbox_stage, 1, TB, 0, c->bbox.p + 6, (int64_t)nb, c->dim, 1, c->bbox.p);
+    c->have_bbox = true;
+  }
+  return c->bbox.p;
+}
+
 int sell_pstride(int ks) {
   int p = 2;
   while (p < ks) p <<= 1;
@@ -385,11 +403,10 @@ void sell_build(Ctx* c) {
   // their columns, so the gathered rows of P are served by the SM's L1 instead of being re-fetched from L2
   const int32_t* order0 = nullptr;
   if (sell_env("REMO_SELL_ORDER", 1)) {
-    double* lohi = scratch<double>(c, 9, 8);
+    const double* lohi = mesh_bbox(c);
     uint64_t* code = scratch<uint64_t>(c, 6, n);
     uint64_t* codes = scratch<uint64_t>(c, 7, n);
     int32_t* ord = scratch<int32_t>(c, 8, n);
-    LAUNCH(c, k_sell_bbox, 1, TB, 0, c->xyz.p, c->nv, c->dim, lohi);
     LAUNCH(c, k_sell_morton, grid_for(n, TB), TB, 0, make_view(c), c->xyz.p, lohi, sell_env("REMO_SELL_CLASSES", 0), code, idx);
     CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, code, codes, idx, ord, n, 0, 64, st));
     c->tmp.ensure(bytes, st);

@@ -206,140 +206,183 @@ __global__ void __launch_bounds__(TB) k_spmm_p(const int64_t* __restrict__ rowpt
 }
 
 // ------------------------------------------------------------------------------------------------
-// vector kernels: thread = (row group, r) with r = threadIdx % KP
+// vector kernels.  The blocks X, R, Z, Q (row stride ks) are walked as FLAT arrays of W-wide elements (W = 2: double2,
+// ks even; W = 1 only for a single right-hand side), so every lane is active and every access is a coalesced 16-byte
+// one whatever ks is (the former (row, column) thread layout left 2 of 8 lanes idle at ks = 6 and reached 3.9 TB/s; flat:
+// ~6 TB/s).  The grid holds a multiple of hc = ks / W threads, so a thread keeps the same column pair for its whole
+// stride loop (its alpha / beta and dot accumulators live in registers) and its row index advances by a constant.
+// P has its own row stride kps (sell.cu).
 // ------------------------------------------------------------------------------------------------
-template <int KP>
-__device__ __forceinline__ void block_partials(double a, double b, double* __restrict__ partial, int nslots) {
-  // threads with equal (threadIdx % KP) hold the same column
-  __shared__ double sh[2][TB];
-  sh[0][threadIdx.x] = a;
-  sh[1][threadIdx.x] = b;
+template <int W> struct VecT { typedef double2 T; };
+template <> struct VecT<1> { typedef double T; };
+__device__ __forceinline__ double lo(double v) { return v; }
+__device__ __forceinline__ double hi(double) { return 0.0; }
+__device__ __forceinline__ double lo(double2 v) { return v.x; }
+__device__ __forceinline__ double hi(double2 v) { return v.y; }
+template <int W> __device__ __forceinline__ typename VecT<W>::T mk(double a, double b);
+template <> __device__ __forceinline__ double mk<1>(double a, double) { return a; }
+template <> __device__ __forceinline__ double2 mk<2>(double a, double b) { return make_double2(a, b); }
+
+// per-column block partials: thread t of block b holds column pair (b * TB + t) % hc; summed in ascending t (fixed order)
+template <int W>
+__device__ __forceinline__ void flat_partials(double a0, double a1, double b0, double b1, int hc, double* __restrict__ partial,
+                                              int nslots) {
+  __shared__ double sh[4][TB];
+  sh[0][threadIdx.x] = a0; sh[1][threadIdx.x] = a1; sh[2][threadIdx.x] = b0; sh[3][threadIdx.x] = b1;
   __syncthreads();
-  if (threadIdx.x < KP) {
-    double ta = 0.0, tb = 0.0;
-    for (int i = threadIdx.x; i < TB; i += KP) { ta += sh[0][i]; tb += sh[1][i]; }
-    partial[((int64_t)blockIdx.x * 2 + 0) * KMAX + threadIdx.x] = ta;
-    if (nslots > 1) partial[((int64_t)blockIdx.x * 2 + 1) * KMAX + threadIdx.x] = tb;
+  if ((int)threadIdx.x < hc) {
+    const int first = (int)((hc - (int)(((int64_t)blockIdx.x * TB) % hc) + (int)threadIdx.x) % hc);  // first t with that pair
+    double t0 = 0.0, t1 = 0.0, u0 = 0.0, u1 = 0.0;
+    for (int i = first; i < TB; i += hc) { t0 += sh[0][i]; t1 += sh[1][i]; u0 += sh[2][i]; u1 += sh[3][i]; }
+    const int64_t o = (int64_t)blockIdx.x * 2 * KMAX + W * threadIdx.x;
+    partial[o] = t0;
+    if (W == 2) partial[o + 1] = t1;
+    if (nslots > 1) {
+      partial[o + KMAX] = u0;
+      if (W == 2) partial[o + KMAX + 1] = u1;
+    }
   }
 }
 
 // X = 0, R = masked F, Z = dinv R and P = Z on rows >= tail_from; partials: [0] = r.r (= b.b), [1] = r.z over those rows
-template <int KP>
+template <int W>
 __global__ void __launch_bounds__(TB) k_init(const double* __restrict__ F, const uint8_t* __restrict__ constrained,
                                              const double* __restrict__ dinv, double* __restrict__ X, double* __restrict__ R,
-                                             double* __restrict__ Z, double* __restrict__ P, int k, int kps, int64_t n,
+                                             double* __restrict__ Z, double* __restrict__ P, int ks, int kps, int64_t n,
                                              int64_t tail_from, double* __restrict__ partial) {
-  const int r = threadIdx.x % KP, g = threadIdx.x / KP;
-  constexpr int G = TB / KP;
-  double rr = 0.0, rz = 0.0;
-  if (r < k)
-    for (int64_t i = (int64_t)blockIdx.x * G + g; i < n; i += (int64_t)gridDim.x * G) {
-      const int64_t idx = i * k + r;
-      const double f = constrained[i] ? 0.0 : F[idx];
-      X[idx] = 0.0;
-      R[idx] = f;
-      rr = fma(f, f, rr);
-      if (i >= tail_from) {  // rows preconditioned by their diagonal: all rows ("local"), the high-order rows ("multigrid")
-        const double z = dinv[i] * f;
-        Z[idx] = z;
-        P[i * kps + r] = z;
-        rz = fma(f, z, rz);
-      }
+  typedef typename VecT<W>::T V;
+  const int hc = ks / W;
+  const int64_t T = (int64_t)gridDim.x * TB, gt = (int64_t)blockIdx.x * TB + threadIdx.x;
+  const int cp = (int)(gt % hc);
+  const int64_t total = n * hc, di = T / hc;
+  double rr0 = 0.0, rr1 = 0.0, rz0 = 0.0, rz1 = 0.0;
+  int64_t i = gt / hc;
+  for (int64_t e = gt; e < total; e += T, i += di) {
+    V f = reinterpret_cast<const V*>(F)[e];
+    if (constrained[i]) f = mk<W>(0.0, 0.0);
+    reinterpret_cast<V*>(X)[e] = mk<W>(0.0, 0.0);
+    reinterpret_cast<V*>(R)[e] = f;
+    rr0 = fma(lo(f), lo(f), rr0); rr1 = fma(hi(f), hi(f), rr1);
+    if (i >= tail_from) {  // rows preconditioned by their diagonal: all rows ("local"), the high-order rows ("multigrid")
+      const double d = dinv[i];
+      const V z = mk<W>(d * lo(f), d * hi(f));
+      reinterpret_cast<V*>(Z)[e] = z;
+      reinterpret_cast<V*>(P)[i * (kps / W) + cp] = z;
+      rz0 = fma(lo(f), lo(z), rz0); rz1 = fma(hi(f), hi(z), rz1);
     }
-  block_partials<KP>(rr, rz, partial, 2);
+  }
+  flat_partials<W>(rr0, rr1, rz0, rz1, hc, partial, 2);
 }
 
 // x += alpha p ; r -= alpha q ; z = dinv r on rows >= tail_from ; partials [0] = r.r, [1] = r.z over those rows
-template <int KP>
+template <int W>
 __global__ void __launch_bounds__(TB) k_update_xr(double* __restrict__ X, double* __restrict__ R, const double* __restrict__ P,
                                                   const double* __restrict__ Q, const double* __restrict__ dinv,
-                                                  double* __restrict__ Z, const double* __restrict__ scal, int k, int kps,
+                                                  double* __restrict__ Z, const double* __restrict__ scal, int ks, int kps,
                                                   int64_t n, int64_t tail_from, double* __restrict__ partial) {
-  const int r = threadIdx.x % KP, g = threadIdx.x / KP;
-  constexpr int G = TB / KP;
-  double rr = 0.0, rz = 0.0;
-  if (r < k) {
-    const double alpha = scal[S_ALPHA * KMAX + r];
-    for (int64_t i = (int64_t)blockIdx.x * G + g; i < n; i += (int64_t)gridDim.x * G) {
-      const int64_t idx = i * k + r;
-      X[idx] = fma(alpha, P[i * kps + r], X[idx]);
-      const double res = fma(-alpha, Q[idx], R[idx]);
-      R[idx] = res;
-      rr = fma(res, res, rr);
-      if (i >= tail_from) {
-        const double z = dinv[i] * res;
-        Z[idx] = z;
-        rz = fma(res, z, rz);
-      }
+  typedef typename VecT<W>::T V;
+  const int hc = ks / W;
+  const int64_t T = (int64_t)gridDim.x * TB, gt = (int64_t)blockIdx.x * TB + threadIdx.x;
+  const int cp = (int)(gt % hc);
+  const int64_t total = n * hc, di = T / hc;
+  const double al0 = scal[S_ALPHA * KMAX + W * cp], al1 = (W == 2) ? scal[S_ALPHA * KMAX + W * cp + 1] : 0.0;
+  double rr0 = 0.0, rr1 = 0.0, rz0 = 0.0, rz1 = 0.0;
+  int64_t i = gt / hc;
+  for (int64_t e = gt; e < total; e += T, i += di) {
+    const V p = reinterpret_cast<const V*>(P)[i * (kps / W) + cp];
+    const V q = reinterpret_cast<const V*>(Q)[e];
+    const V x = reinterpret_cast<const V*>(X)[e];
+    const V r = reinterpret_cast<const V*>(R)[e];
+    reinterpret_cast<V*>(X)[e] = mk<W>(fma(al0, lo(p), lo(x)), fma(al1, hi(p), hi(x)));
+    const double s0 = fma(-al0, lo(q), lo(r)), s1 = fma(-al1, hi(q), hi(r));
+    reinterpret_cast<V*>(R)[e] = mk<W>(s0, s1);
+    rr0 = fma(s0, s0, rr0); rr1 = fma(s1, s1, rr1);
+    if (i >= tail_from) {
+      const double d = dinv[i];
+      const double z0 = d * s0, z1 = d * s1;
+      reinterpret_cast<V*>(Z)[e] = mk<W>(z0, z1);
+      rz0 = fma(s0, z0, rz0); rz1 = fma(s1, z1, rz1);
     }
   }
-  block_partials<KP>(rr, rz, partial, 2);
+  flat_partials<W>(rr0, rr1, rz0, rz1, hc, partial, 2);
 }
 
 // partial [1] += r.z over rows [0, n): the rows preconditioned by the V-cycle (the others were summed by k_update_xr)
-template <int KP>
-__global__ void __launch_bounds__(TB) k_dot_rz(const double* __restrict__ R, const double* __restrict__ Z, int k, int64_t n,
+template <int W>
+__global__ void __launch_bounds__(TB) k_dot_rz(const double* __restrict__ R, const double* __restrict__ Z, int ks, int64_t n,
                                                double* __restrict__ partial) {
-  const int r = threadIdx.x % KP, g = threadIdx.x / KP;
-  constexpr int G = TB / KP;
-  double rz = 0.0;
-  if (r < k)
-    for (int64_t i = (int64_t)blockIdx.x * G + g; i < n; i += (int64_t)gridDim.x * G) rz = fma(R[i * k + r], Z[i * k + r], rz);
-  __shared__ double sh[TB];
-  sh[threadIdx.x] = rz;
+  typedef typename VecT<W>::T V;
+  const int hc = ks / W;
+  const int64_t T = (int64_t)gridDim.x * TB, gt = (int64_t)blockIdx.x * TB + threadIdx.x;
+  const int64_t total = n * hc;
+  double rz0 = 0.0, rz1 = 0.0;
+  for (int64_t e = gt; e < total; e += T) {
+    const V r = reinterpret_cast<const V*>(R)[e], z = reinterpret_cast<const V*>(Z)[e];
+    rz0 = fma(lo(r), lo(z), rz0); rz1 = fma(hi(r), hi(z), rz1);
+  }
+  __shared__ double sh[2][TB];
+  sh[0][threadIdx.x] = rz0; sh[1][threadIdx.x] = rz1;
   __syncthreads();
-  if (threadIdx.x < KP) {
-    double t = 0.0;
-    for (int i = threadIdx.x; i < TB; i += KP) t += sh[i];
-    partial[((int64_t)blockIdx.x * 2 + 1) * KMAX + threadIdx.x] += t;
+  if ((int)threadIdx.x < hc) {
+    const int first = (int)((hc - (int)(((int64_t)blockIdx.x * TB) % hc) + (int)threadIdx.x) % hc);
+    double t0 = 0.0, t1 = 0.0;
+    for (int i = first; i < TB; i += hc) { t0 += sh[0][i]; t1 += sh[1][i]; }
+    const int64_t o = ((int64_t)blockIdx.x * 2 + 1) * KMAX + W * threadIdx.x;
+    partial[o] += t0;
+    if (W == 2) partial[o + 1] += t1;
   }
 }
 
 // p = z + beta p
-template <int KP>
+template <int W>
 __global__ void __launch_bounds__(TB) k_update_p(double* __restrict__ P, const double* __restrict__ Z,
-                                                 const double* __restrict__ scal, int k, int kps, int64_t n) {
-  const int r = threadIdx.x % KP, g = threadIdx.x / KP;
-  constexpr int G = TB / KP;
-  if (r >= k) return;
-  const double beta = scal[S_BETA * KMAX + r];
-  for (int64_t i = (int64_t)blockIdx.x * G + g; i < n; i += (int64_t)gridDim.x * G) {
-    const int64_t ip = i * kps + r;
-    P[ip] = fma(beta, P[ip], Z[i * k + r]);
+                                                 const double* __restrict__ scal, int ks, int kps, int64_t n) {
+  typedef typename VecT<W>::T V;
+  const int hc = ks / W;
+  const int64_t T = (int64_t)gridDim.x * TB, gt = (int64_t)blockIdx.x * TB + threadIdx.x;
+  const int cp = (int)(gt % hc);
+  const int64_t total = n * hc, di = T / hc;
+  const double be0 = scal[S_BETA * KMAX + W * cp], be1 = (W == 2) ? scal[S_BETA * KMAX + W * cp + 1] : 0.0;
+  int64_t i = gt / hc;
+  for (int64_t e = gt; e < total; e += T, i += di) {
+    V* pp = reinterpret_cast<V*>(P) + i * (kps / W) + cp;
+    const V p = *pp, z = reinterpret_cast<const V*>(Z)[e];
+    *pp = mk<W>(fma(be0, lo(p), lo(z)), fma(be1, hi(p), hi(z)));
   }
 }
 
 // ---- one-block scalar kernels: finish the reductions in a fixed order (32 x 32 threads: column r, strip j)
-__device__ __forceinline__ double reduce_partials(const double* __restrict__ partial, int nblk, int stride, int slot) {
-  const int r = threadIdx.x & 31, j = threadIdx.x >> 5;  // blockDim = 1024
-  // four independent accumulators, loads issued 8 deep: the loop is latency bound (L2 round trips), not bandwidth bound.
-  // The summation order is fixed, so the result is still bit-reproducible.
+// 1024 threads = ncol columns (power of two >= the column count) x 1024 / ncol strips: with few right-hand sides the
+// strips are short even when the SpMM grid has thousands of blocks.  Fixed summation order -> bit-reproducible.
+__device__ __forceinline__ double reduce_partials(const double* __restrict__ partial, int nblk, int stride, int slot, int ncol) {
+  const int r = threadIdx.x & (ncol - 1), j = threadIdx.x / ncol, ns = 1024 / ncol;
   double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
   int b = j;
 #pragma unroll 2
-  for (; b + 96 < nblk; b += 128) {
+  for (; b + 3 * ns < nblk; b += 4 * ns) {
     t0 += partial[((int64_t)b * stride + slot) * KMAX + r];
-    t1 += partial[((int64_t)(b + 32) * stride + slot) * KMAX + r];
-    t2 += partial[((int64_t)(b + 64) * stride + slot) * KMAX + r];
-    t3 += partial[((int64_t)(b + 96) * stride + slot) * KMAX + r];
+    t1 += partial[((int64_t)(b + ns) * stride + slot) * KMAX + r];
+    t2 += partial[((int64_t)(b + 2 * ns) * stride + slot) * KMAX + r];
+    t3 += partial[((int64_t)(b + 3 * ns) * stride + slot) * KMAX + r];
   }
-  for (; b < nblk; b += 32) t0 += partial[((int64_t)b * stride + slot) * KMAX + r];
+  for (; b < nblk; b += ns) t0 += partial[((int64_t)b * stride + slot) * KMAX + r];
   const double t = (t0 + t1) + (t2 + t3);
-  __shared__ double sh[32][33];
+  __shared__ double sh[1024];
   __syncthreads();
-  sh[j][r] = t;
+  sh[threadIdx.x] = t;
   __syncthreads();
   double tot = 0.0;
   if (j == 0)
-    for (int q = 0; q < 32; q++) tot += sh[q][r];
-  return tot;  // valid for j == 0
+    for (int q = 0; q < ns; q++) tot += sh[q * ncol + r];
+  return tot;  // valid for threads < ncol (columns >= the column count sum never-written zeros)
 }
 
 // after k_init: bb = rr, rz, active, tolerance
 __global__ void k_scal_init(const double* __restrict__ partial, int nblk, double* __restrict__ scal, int* __restrict__ iters,
-                            int k, double rtol) {
-  const double rr = reduce_partials(partial, nblk, 2, 0);
-  const double rz = reduce_partials(partial, nblk, 2, 1);
+                            int k, double rtol, int ncol) {
+  double rr = reduce_partials(partial, nblk, 2, 0, ncol);
+  double rz = reduce_partials(partial, nblk, 2, 1, ncol);
+  if (threadIdx.x >= ncol) { rr = 0.0; rz = 0.0; }
   if (threadIdx.x < KMAX) {
     const int r = threadIdx.x;
     const bool act = r < k && rr > 0.0;
@@ -355,15 +398,15 @@ __global__ void k_scal_init(const double* __restrict__ partial, int nblk, double
 }
 
 // rz only (general preconditioner path, after the first apply)
-__global__ void k_scal_rz0(const double* __restrict__ partial, int nblk, double* __restrict__ scal) {
-  const double rz = reduce_partials(partial, nblk, 2, 1);
-  if (threadIdx.x < KMAX) scal[S_RZ * KMAX + threadIdx.x] = rz;
+__global__ void k_scal_rz0(const double* __restrict__ partial, int nblk, double* __restrict__ scal, int ncol) {
+  const double rz = reduce_partials(partial, nblk, 2, 1, ncol);
+  if (threadIdx.x < ncol) scal[S_RZ * KMAX + threadIdx.x] = rz;
 }
 
 // after the SpMM: alpha = rz / p.q
-__global__ void k_scal_alpha(const double* __restrict__ partial, int nblk, double* __restrict__ scal) {
-  const double pq = reduce_partials(partial, nblk, 1, 0);
-  if (threadIdx.x < KMAX) {
+__global__ void k_scal_alpha(const double* __restrict__ partial, int nblk, double* __restrict__ scal, int ncol) {
+  const double pq = reduce_partials(partial, nblk, 1, 0, ncol);
+  if (threadIdx.x < ncol) {
     const int r = threadIdx.x;
     const bool act = scal[S_ACTIVE * KMAX + r] != 0.0;
     scal[S_PQ * KMAX + r] = pq;
@@ -372,10 +415,11 @@ __global__ void k_scal_alpha(const double* __restrict__ partial, int nblk, doubl
 }
 
 // after the residual update (+ preconditioner): rr, convergence, beta = rz_new / rz
-__global__ void k_scal_beta(const double* __restrict__ partial, int nblk, double* __restrict__ scal, int* __restrict__ iters) {
-  const double rr = reduce_partials(partial, nblk, 2, 0);
-  const double rzn = reduce_partials(partial, nblk, 2, 1);
-  if (threadIdx.x < KMAX) {
+__global__ void k_scal_beta(const double* __restrict__ partial, int nblk, double* __restrict__ scal, int* __restrict__ iters,
+                            int ncol) {
+  const double rr = reduce_partials(partial, nblk, 2, 0, ncol);
+  const double rzn = reduce_partials(partial, nblk, 2, 1, ncol);
+  if (threadIdx.x < ncol) {
     const int r = threadIdx.x;
     bool act = scal[S_ACTIVE * KMAX + r] != 0.0;
     if (act) {
@@ -480,7 +524,16 @@ int kp_for(int k) {
     default: { constexpr int KP = 32; CALL; } break; \
   }
 
-int vec_grid(Ctx* c) { return c->num_sms * 8; }
+// grid of the flat vector kernels: grid * TB threads must be a multiple of hc = ks / W (see above)
+int vec_grid(Ctx* c, int ks) {
+  int odd = (ks & 1) ? ks : ks / 2;
+  while ((odd & 1) == 0) odd >>= 1;
+  const int g = c->num_sms * 8;
+  return (g + odd - 1) / odd * odd;
+}
+#define DISPATCH_W(ks, CALL)                      \
+  if ((ks) & 1) { constexpr int W = 1; CALL; }    \
+  else { constexpr int W = 2; CALL; }
 bool use_sell(const Ctx* c, int nrhs, const double* P) { return c->have_sell && c->pstride >= 2 && (nrhs & 1) == 0 && P == c->P.p; }
 int spmm_grid(Ctx* c, int nrhs) { return use_sell(c, nrhs, c->P.p) ? sell_grid(c) : c->num_sms * 8; }
 
@@ -505,7 +558,7 @@ void alloc_solver_state(Ctx* c, int nrhs) {
   c->pstride = (spmm_variant() >= 5 && nrhs >= 2 && (nrhs & 1) == 0) ? sell_pstride(nrhs) : nrhs;
   c->P.ensure((size_t)c->ndof * c->pstride, st);
   if (c->pstride != nrhs) CK(cudaMemsetAsync(c->P.p, 0, (size_t)c->ndof * c->pstride * sizeof(double), st));
-  c->partial.ensure((size_t)std::max(vec_grid(c), c->num_sms * 64) * 2 * KMAX, st);  // room for any SpMM grid (sell.cu caps its own)
+  c->partial.ensure((size_t)std::max(vec_grid(c, nrhs), c->num_sms * 64) * 2 * KMAX, st);  // room for any SpMM grid (sell.cu caps its own)
   CK(cudaMemsetAsync(c->partial.p, 0, c->partial.n * sizeof(double), st));
   c->scal.ensure(S_NSLOT * KMAX, st);
   c->iters_d.ensure(KMAX, st);
@@ -566,10 +619,9 @@ void launch_spmm(Ctx* c, const double* P, double* Q, int nrhs) {
 }
 
 void launch_vector_updates(Ctx* c, int nrhs) {
-  const int kp = kp_for(nrhs);
-  const int grid = vec_grid(c);
-  DISPATCH_KP(kp, (k_update_xr<KP><<<grid, TB, 0, c->stream>>>(c->X.p, c->R.p, c->P.p, c->Q.p, c->dinv.p, c->Z.p, c->scal.p, nrhs, c->pstride, c->ndof, (int64_t)0, c->partial.p)));
-  DISPATCH_KP(kp, (k_update_p<KP><<<grid, TB, 0, c->stream>>>(c->P.p, c->Z.p, c->scal.p, nrhs, c->pstride, c->ndof)));
+  const int grid = vec_grid(c, nrhs);
+  DISPATCH_W(nrhs, (k_update_xr<W><<<grid, TB, 0, c->stream>>>(c->X.p, c->R.p, c->P.p, c->Q.p, c->dinv.p, c->Z.p, c->scal.p, nrhs, c->pstride, c->ndof, (int64_t)0, c->partial.p)));
+  DISPATCH_W(nrhs, (k_update_p<W><<<grid, TB, 0, c->stream>>>(c->P.p, c->Z.p, c->scal.p, nrhs, c->pstride, c->ndof)));
   c->launches += 2;
   CK(cudaGetLastError());
 }
@@ -626,20 +678,20 @@ int solve(Ctx* c, double rtol, int maxit, int* iters, double* relres) {
   cudaStream_t st = c->stream;
   const int k = c->nrhs, kp = kp_for(k);
   const int64_t n = c->ndof;
-  const int vg = vec_grid(c), sg = spmm_grid(c, k);
+  const int vg = vec_grid(c, k), sg = spmm_grid(c, k);
   const int jac = (c->pkind == REMO_PRECOND_LOCAL) ? 1 : 0;
   const int64_t tail = jac ? 0 : c->nv;  // rows >= tail: z = D^-1 r fused into the vector kernels; rows < tail: V-cycle
 
   const int kps = c->pstride;
-  DISPATCH_KP(kp, (k_init<KP><<<vg, TB, 0, st>>>(c->F.p, c->constrained.p, c->dinv.p, c->X.p, c->R.p, c->Z.p, c->P.p, k, kps, n, tail, c->partial.p)));
+  DISPATCH_W(k, (k_init<W><<<vg, TB, 0, st>>>(c->F.p, c->constrained.p, c->dinv.p, c->X.p, c->R.p, c->Z.p, c->P.p, k, kps, n, tail, c->partial.p)));
   c->launches++;
   if (!jac) {
     amg_apply(c, c->R.p, c->Z.p, k);
-    DISPATCH_KP(kp, (k_dot_rz<KP><<<vg, TB, 0, st>>>(c->R.p, c->Z.p, k, tail, c->partial.p)));
+    DISPATCH_W(k, (k_dot_rz<W><<<vg, TB, 0, st>>>(c->R.p, c->Z.p, k, tail, c->partial.p)));
     CK(cudaMemcpy2DAsync(c->P.p, (size_t)kps * sizeof(double), c->Z.p, (size_t)k * sizeof(double), (size_t)k * sizeof(double), (size_t)tail, cudaMemcpyDeviceToDevice, st));
     c->launches++;
   }
-  k_scal_init<<<1, 1024, 0, st>>>(c->partial.p, vg, c->scal.p, c->iters_d.p, k, rtol);
+  k_scal_init<<<1, 1024, 0, st>>>(c->partial.p, vg, c->scal.p, c->iters_d.p, k, rtol, kp);
   c->launches++;
   CK(cudaGetLastError());
 
@@ -662,15 +714,15 @@ int solve(Ctx* c, double rtol, int maxit, int* iters, double* relres) {
     }
     launch_spmm(c, c->P.p, c->Q.p, k);
     if (c->prof) CK(cudaEventRecord(c->prof_ev[pe + 1], st));
-    k_scal_alpha<<<1, 1024, 0, st>>>(c->partial.p, sg, c->scal.p);
-    DISPATCH_KP(kp, (k_update_xr<KP><<<vg, TB, 0, st>>>(c->X.p, c->R.p, c->P.p, c->Q.p, c->dinv.p, c->Z.p, c->scal.p, k, kps, n, tail, c->partial.p)));
+    k_scal_alpha<<<1, 1024, 0, st>>>(c->partial.p, sg, c->scal.p, kp);
+    DISPATCH_W(k, (k_update_xr<W><<<vg, TB, 0, st>>>(c->X.p, c->R.p, c->P.p, c->Q.p, c->dinv.p, c->Z.p, c->scal.p, k, kps, n, tail, c->partial.p)));
     if (!jac) {
       amg_apply(c, c->R.p, c->Z.p, k);
-      DISPATCH_KP(kp, (k_dot_rz<KP><<<vg, TB, 0, st>>>(c->R.p, c->Z.p, k, tail, c->partial.p)));
+      DISPATCH_W(k, (k_dot_rz<W><<<vg, TB, 0, st>>>(c->R.p, c->Z.p, k, tail, c->partial.p)));
       c->launches++;
     }
-    k_scal_beta<<<1, 1024, 0, st>>>(c->partial.p, vg, c->scal.p, c->iters_d.p);
-    DISPATCH_KP(kp, (k_update_p<KP><<<vg, TB, 0, st>>>(c->P.p, c->Z.p, c->scal.p, k, kps, n)));
+    k_scal_beta<<<1, 1024, 0, st>>>(c->partial.p, vg, c->scal.p, c->iters_d.p, kp);
+    DISPATCH_W(k, (k_update_p<W><<<vg, TB, 0, st>>>(c->P.p, c->Z.p, c->scal.p, k, kps, n)));
     c->launches += 4;
   };
 
