@@ -1,20 +1,22 @@
 // Sliced-ELLPACK copy of the stiffness matrix for the multi-right-hand-side PCG SpMM (Q = A P + fused p.q).
 //
-// Why a second layout.  The CSR SpMM (solver.cu k_spmm_p) is bound by the SM's L1 data pipe, not by HBM
-// (profiles/r01_notes.md): per matrix entry it spends one wavefront on the gathered row of P -- 1.4 when the 48-byte
-// rows of a 6-column block straddle 128-byte lines -- plus 0.4 wavefronts of shuffles that hand the (col, val) pairs of a
-// row to the lanes of its group, plus the coalesced (col, val) loads.  This layout removes everything but the gather:
+// Why a second layout.  The CSR SpMM (solver.cu k_spmm_p) sits at 90 % of the SM's L1 data pipe (profiles/r01_notes.md):
+// per matrix entry one wavefront for the gathered row of P -- 1.4 when the 48-byte rows of a 6-column block straddle
+// 128-byte lines -- plus the shuffles that hand the (col, val) pairs of a row to the lanes of its group.  Here:
 //   * slices of 8 rows (one warp = 8 groups of 4 lanes at 5..8 right-hand sides); inside a slice the entries are stored
-//     in chunks of 4 per row, rows interleaved: col[chunk][row 0..7][4] (int32), val[chunk][row 0..7][4] (fp64).  All
-//     lanes of a group read the SAME 16 bytes of columns / 32 bytes of values (a broadcast inside one wavefront) and the
-//     8 groups of the warp read 128 / 256 contiguous bytes: 3 wavefronts per 32 entries, no shuffles;
-//   * rows are sorted by length inside windows of 2048 rows (SELL-C-sigma), so a slice is padded only to the longest
-//     of 8 similar rows and the 8 groups of a warp run the same trip count (the CSR kernel's warps ran as long as the
-//     longest of 8 unrelated rows); padding entries are (own row, 0.0);
+//     in chunks of 4 per row, rows interleaved: col[chunk][row 0..7][4] (int32), val[chunk][row 0..7][4] (fp64), so the
+//     (col, val) data of a warp step are 384 contiguous bytes and need no shuffles;
+//   * rows are taken in Morton order of their dof location and sorted by length inside windows of 2048 rows
+//     (SELL-C-sigma): a slice is padded only to the longest of 8 similar rows (2 % padding on the bench meshes) and the
+//     8 groups of a warp run the same trip count; padding entries are (own row, 0.0);
 //   * the search directions P are kept in their own block with a power-of-two row stride (64 bytes for 5..8 columns),
-//     so a gathered row never straddles a line: exactly one wavefront per matrix entry.
+//     so a gathered row never straddles a line.
+// Two kernels read it: k_spmm_stream8 (P stride 8, i.e. 5..8 right-hand sides: per-warp contiguous chunk ranges streamed
+// through a cp.async ring in shared memory) and the generic k_spmm_sell<KS> (KS/2 lanes per row, register prefetch of
+// the next chunk) for the other strides.  Measured on B200 at 4.8 M dofs (136.9 M non-zeros): 5 RHS 1.04 -> 0.865 ms
+// (36.5 % of the measured HBM peak by algorithmic bytes), 8 RHS 0.856 ms (41 %), 2 RHS 0.39 ms (72 %).
 // The CSR arrays stay the assembly target and the parity export (remo_matrix_get); this copy is made once per matrix
-// by remo_precond_setup (a radix sort of ndof keys + one streaming pass over the matrix).
+// by remo_precond_setup (two radix sorts of ndof keys + one streaming pass over the matrix, ~5 ms at 4.8 M dofs).
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -93,7 +95,7 @@ __global__ void k_bbox_stage(const double* __restrict__ in, int64_t count, int d
   }
 }
 
-__global__ void k_sell_morton(SpaceView s, const double* __restrict__ xyz, const double* __restrict__ lohi, int classes,
+__global__ void k_sell_morton(SpaceView s, const double* __restrict__ xyz, const double* __restrict__ lohi,
                               uint64_t* __restrict__ code, int32_t* __restrict__ idx) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= s.ndof) return;
@@ -122,10 +124,7 @@ __global__ void k_sell_morton(SpaceView s, const double* __restrict__ xyz, const
     const uint64_t q = (uint64_t)fmin(fmax(t * 2097151.0, 0.0), 2097151.0);
     c |= spread21s(q) << d;
   }
-  // class-major: vertex / edge / face rows have very different lengths (80 / 25 / 15 entries at order 2..3); keeping the
-  // classes apart lets a SMALL sorting window (which preserves the spatial order) pad the slices well
-  const uint64_t cls = i < s.nv ? 0 : (i < s.face_base ? 1 : 2);
-  code[i] = classes ? ((cls << 62) | (c >> 2)) : c;
+  code[i] = c;
   idx[i] = (int32_t)i;
 }
 
@@ -284,7 +283,7 @@ __global__ void __launch_bounds__(256, MINB) k_spmm_stream8(const int64_t* __res
                                                             const double* __restrict__ sval, const int32_t* __restrict__ srow,
                                                             const uint8_t* __restrict__ constrained, const double* __restrict__ P,
                                                             double* __restrict__ Q, int ks, double* __restrict__ partial,
-                                                            const int64_t* __restrict__ wpart, int smap) {
+                                                            const int64_t* __restrict__ wpart) {
   constexpr int CHB = 384;  // bytes of one chunk: 8 rows x 4 columns (int32) + 8 rows x 4 values (fp64)
   __shared__ __align__(16) unsigned char ring[8][D][CHB];
   __shared__ double sh[2][256];
@@ -293,9 +292,7 @@ __global__ void __launch_bounds__(256, MINB) k_spmm_stream8(const int64_t* __res
   const bool on = 2 * l < ks;
   const double2* __restrict__ P2 = reinterpret_cast<const double2*>(P) + l;
   double dot0 = 0.0, dot1 = 0.0;
-  // smap > 0: the CTAs b, b + smap, b + 2 smap, ... (the ones a first wave puts on one SM) own adjacent ranges
-  const int64_t vb = smap > 0 ? (int64_t)(blockIdx.x % smap) * (gridDim.x / smap) + blockIdx.x / smap : blockIdx.x;
-  const int64_t gw = vb * 8 + w;
+  const int64_t gw = (int64_t)blockIdx.x * 8 + w;
   int64_t s = wpart[gw];
   const int64_t s_end = wpart[gw + 1];
   if (s < s_end) {
@@ -407,10 +404,10 @@ void sell_build(Ctx* c) {
     uint64_t* code = scratch<uint64_t>(c, 6, n);
     uint64_t* codes = scratch<uint64_t>(c, 7, n);
     int32_t* ord = scratch<int32_t>(c, 8, n);
-    LAUNCH(c, k_sell_morton, grid_for(n, TB), TB, 0, make_view(c), c->xyz.p, lohi, sell_env("REMO_SELL_CLASSES", 0), code, idx);
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, code, codes, idx, ord, n, 0, 64, st));
+    LAUNCH(c, k_sell_morton, grid_for(n, TB), TB, 0, make_view(c), c->xyz.p, lohi, code, idx);
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, code, codes, idx, ord, n, 0, 63, st));
     c->tmp.ensure(bytes, st);
-    CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, code, codes, idx, ord, n, 0, 64, st));
+    CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, code, codes, idx, ord, n, 0, 63, st));
     c->launches += 4;
     order0 = ord;
   }
@@ -441,8 +438,7 @@ void sell_build(Ctx* c) {
   {
     // blocked distribution: `waves` CTAs per resident CTA slot; 0 = grid-strided rows
     const int waves = sell_env("REMO_SELL_WAVES", 4);
-    const int tbk = sell_env("REMO_SELL_TB", 256);
-    c->sell_nparts = waves > 0 ? std::min(c->num_sms * (1024 / tbk) * waves, c->num_sms * 64) : 0;
+    c->sell_nparts = waves > 0 ? std::min(c->num_sms * 4 * waves, c->num_sms * 64) : 0;
     if (c->sell_nparts > 0) {
       c->sell_part.ensure(c->sell_nparts + 1, st);
       LAUNCH(c, k_sell_partition, grid_for(c->sell_nparts + 1, TB), TB, 0, c->sell_ptr.p, nslices, c->sell_nparts, c->sell_part.p);
@@ -467,7 +463,7 @@ static bool sell_stream(const Ctx* c) { return c->pstride == 8 && sell_env("REMO
 
 int sell_grid(const Ctx* c) {
   if (sell_stream(c)) return c->sell_sgrid;
-  return c->sell_nparts > 0 ? c->sell_nparts : c->num_sms * 8 * 256 / sell_env("REMO_SELL_TB", 256);
+  return c->sell_nparts > 0 ? c->sell_nparts : c->num_sms * 8;
 }
 
 void launch_spmm_sell(Ctx* c, const double* P, double* Q, int ks, int pstride) {
@@ -476,32 +472,19 @@ void launch_spmm_sell(Ctx* c, const double* P, double* Q, int ks, int pstride) {
   auto* cs = c->constrained.p;
   double* pt = c->partial.p;
   const int64_t ns = c->sell_slots;
-  static int tbk = -1;
-  if (tbk < 0) tbk = sell_env("REMO_SELL_TB", 256);
   const int64_t* part = c->sell_nparts > 0 ? c->sell_part.p : nullptr;
   const int grid = sell_grid(c);
   if (sell_stream(c)) {
-    static int depth = -1;
-    if (depth < 0) depth = sell_env("REMO_SELL_DEPTH", 4);
-    static int minb = -1;
-    if (minb < 0) minb = sell_env("REMO_SELL_SMINB", 4);
-    static int smap = -1;
-    if (smap < 0) smap = sell_env("REMO_SELL_SMAP", 0) ? c->num_sms : 0;
-#define STREAM_CASE(D_, M_) k_spmm_stream8<D_, M_><<<grid, 256, 0, st>>>(sp, sc, sv, sr, cs, P, Q, ks, pt, c->sell_wpart.p, smap)
-    if (minb <= 4) { if (depth >= 8) STREAM_CASE(8, 4); else STREAM_CASE(4, 4); }
-    else if (minb == 5) { if (depth >= 8) STREAM_CASE(8, 5); else STREAM_CASE(4, 5); }
-    else { if (depth >= 8) STREAM_CASE(8, 6); else STREAM_CASE(4, 6); }
-#undef STREAM_CASE
+    // ring depth 4: three chunks ahead cover the DRAM latency of the matrix stream (depth 8 measured equal); 64 registers,
+    // 4 CTAs per SM -- tighter register caps spill and run 1.5x slower, a software-pipelined variant with 8 gathers in
+    // flight per lane needs 80-94 registers and is 1.3-1.8x slower (fewer warps): profiles/r01_notes.md
+    k_spmm_stream8<4, 4><<<grid, 256, 0, st>>>(sp, sc, sv, sr, cs, P, Q, ks, pt, c->sell_wpart.p);
     c->launches++;
     CK(cudaGetLastError());
     return;
   }
-#define SELL_CASE(KS_)                                                                                              \
-  case KS_:                                                                                                         \
-    if (tbk == 1024) k_spmm_sell<KS_, 1024, 1, 1><<<grid, 1024, 0, st>>>(sp, sc, sv, sr, cs, P, Q, ks, ns, pt, part);   \
-    else if (tbk == 512) k_spmm_sell<KS_, 512, 2, 1><<<grid, 512, 0, st>>>(sp, sc, sv, sr, cs, P, Q, ks, ns, pt, part); \
-    else k_spmm_sell<KS_, 256, 4, 1><<<grid, 256, 0, st>>>(sp, sc, sv, sr, cs, P, Q, ks, ns, pt, part);                 \
-    break;
+#define SELL_CASE(KS_) \
+  case KS_: k_spmm_sell<KS_, 256, 4, 1><<<grid, 256, 0, st>>>(sp, sc, sv, sr, cs, P, Q, ks, ns, pt, part); break;
   switch (pstride) {
     SELL_CASE(2) SELL_CASE(4) SELL_CASE(8) SELL_CASE(16) SELL_CASE(32)
     default: FAIL(REMO_ERR_ARG, "launch_spmm_sell: unsupported stride %d", pstride);

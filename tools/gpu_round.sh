@@ -1,7 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for c in 1 2 3; do
-REMO_BENCH_DEBUG=1 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --contexts $c > gpurun_out/bench_5M_c$c.json 2> gpurun_out/bench_5M_c$c.err; tail -2 gpurun_out/bench_5M_c$c.err
-python -c "
-import json; d=json.load(open('gpurun_out/bench_5M_c$c.json')); print('contexts', $c, 'value', d['value'], 'ms/step', d['ms_per_step'], 'e2e', d['e2e']['value'], d['config']['stage_ms'])"
-done
+: > gpurun_out/sweep9.log
+run() { echo "$*" >> gpurun_out/sweep9.log; env "$@" timeout 300 python tools/spmm_probe.py --ks 5,8 2>&1 | grep "^k=\|rror" >> gpurun_out/sweep9.log; }
+for p in 0 2 3 4; do run REMO_SELL_PIPE=$p REMO_PROBE_SIZE=5M; done
+for p in 0 3; do run REMO_SELL_PIPE=$p REMO_PROBE_SIZE=1M; done
+cat gpurun_out/sweep9.log
+REMO_SELL_PIPE=3 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
