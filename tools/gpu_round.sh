@@ -1,8 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-: > gpurun_out/sweep9.log
-run() { echo "$*" >> gpurun_out/sweep9.log; env "$@" timeout 300 python tools/spmm_probe.py --ks 5,8 2>&1 | grep "^k=\|rror" >> gpurun_out/sweep9.log; }
-for p in 0 2 3 4; do run REMO_SELL_PIPE=$p REMO_PROBE_SIZE=5M; done
-for p in 0 3; do run REMO_SELL_PIPE=$p REMO_PROBE_SIZE=1M; done
-cat gpurun_out/sweep9.log
-REMO_SELL_PIPE=3 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log; tail -3 gpurun_out/smoke.log
+python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_default.err
+python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
+cat gpurun_out/bench_ref.json | cut -c1-600
