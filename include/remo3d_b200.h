@@ -115,6 +115,15 @@ int remo_solution_get(void* ctx, int rhs, double* u);
  *   which = 1: numeric assembly (remo_assemble's kernels)
  *   which = 2: PCG vector update kernels for nrhs columns                                       */
 int remo_kernel_time(void* ctx, int which, int nrhs, int reps, float* ms);
+
+/* Parity hook (tests): one launch of the PCG's SpMM on caller-supplied search directions.
+ *   p  : host, ndof x nrhs row-major (the nrhs values of a dof contiguous)
+ *   q  : host, ndof x nrhs row-major, receives Q = A P with the rows of constrained dofs set to 0
+ *   pq : host, nrhs, receives the fused dots p_r . q_r (block partials finished in a fixed order)
+ * Runs exactly the kernel remo_solve would use for this nrhs (SELL streaming / SELL generic / CSR), including the
+ * internal strides; needs remo_assemble (sets up the "local" preconditioner if none is set).  Invalidates the
+ * right-hand sides and the solution of the context.                                                            */
+int remo_spmm_apply(void* ctx, int nrhs, const double* p, double* q, double* pq);
 /* Solver tunables (defaults in parentheses): "amg_sweeps" (1) pre = post damped-Jacobi sweeps per AMG level,
  * "amg_alpha" (1.5) scaling of the coarse-grid correction, "amg_omega_scale" (1.0) weight of the l1-Jacobi sweeps,
  * must be <= 1 (changing it invalidates the preconditioner: call remo_precond_setup again).                        */

@@ -37,6 +37,7 @@ SIGNATURES = {
     "remo_apparent_resistivity": (C.c_int, [_p, C.c_int, _p, _p, _p, _p, C.c_double, _p]),
     "remo_solution_get": (C.c_int, [_p, C.c_int, _p]),
     "remo_kernel_time": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "remo_spmm_apply": (C.c_int, [_p, C.c_int, _p, _p, _p]),
     "remo_set_option": (C.c_int, [_p, C.c_char_p, C.c_double]),
     "remo_profile": (C.c_int, [_p, C.c_int]),
     "remo_profile_get": (C.c_int, [_p, C.POINTER(C.c_double), _i64p]),
@@ -205,6 +206,16 @@ class Context:
         ms = C.c_float()
         self._ck(self.lib.remo_kernel_time(self.h, int(which), int(nrhs), int(reps), C.byref(ms)))
         return ms.value
+
+    def spmm_apply(self, p):
+        """One launch of the PCG SpMM on host search directions p (ndof x nrhs) -> (Q = A P, fused dots p.q)."""
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        if p.ndim != 2 or p.shape[0] != self.ndof:
+            raise ValueError("spmm_apply: p must be ndof x nrhs")
+        q = np.empty_like(p)
+        pq = np.empty(p.shape[1])
+        self._ck(self.lib.remo_spmm_apply(self.h, p.shape[1], p.ctypes.data, q.ctypes.data, pq.ctypes.data))
+        return q, pq
 
     def set_option(self, name, value):
         self._ck(self.lib.remo_set_option(self.h, name.encode(), float(value)))

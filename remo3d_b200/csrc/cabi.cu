@@ -318,6 +318,34 @@ int remo_kernel_time(void* vctx, int which, int nrhs, int reps, float* ms) {
   });
 }
 
+int remo_spmm_apply(void* vctx, int nrhs, const double* p, double* q, double* pq) {
+  return guarded(vctx, [&](Ctx* c) {
+    if (!c->have_matrix) FAIL(REMO_ERR_STATE, "remo_spmm_apply: assemble a matrix first");
+    if (nrhs < 1 || nrhs > REMO_MAX_RHS || !p || !q || !pq) FAIL(REMO_ERR_ARG, "remo_spmm_apply: bad arguments");
+    cudaStream_t st = c->stream;
+    if (c->pkind < 0) precond_setup(c, REMO_PRECOND_LOCAL);
+    const int ks = solver_stride(nrhs);
+    alloc_solver_state(c, ks);
+    c->nrhs_user = nrhs;
+    c->have_rhs = c->have_solution = false;
+    const size_t w = (size_t)nrhs * sizeof(double);
+    CK(cudaMemsetAsync(c->P.p, 0, (size_t)c->ndof * c->pstride * sizeof(double), st));
+    CK(cudaMemcpy2DAsync(c->P.p, (size_t)c->pstride * sizeof(double), p, w, w, (size_t)c->ndof, cudaMemcpyDefault, st));
+    launch_spmm(c, c->P.p, c->Q.p, ks);
+    CK(cudaMemcpy2DAsync(q, w, c->Q.p, (size_t)ks * sizeof(double), w, (size_t)c->ndof, cudaMemcpyDefault, st));
+    const int nblk = spmm_blocks(c, ks);
+    std::vector<double> part((size_t)nblk * REMO_MAX_RHS);
+    CK(cudaMemcpyAsync(part.data(), c->partial.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int r = 0; r < nrhs; r++) {
+      double t = 0.0;
+      for (int b = 0; b < nblk; b++) t += part[(size_t)b * REMO_MAX_RHS + r];
+      pq[r] = t;
+    }
+    return REMO_OK;
+  });
+}
+
 int remo_set_option(void* vctx, const char* name, double value) {
   return guarded(vctx, [&](Ctx* c) {
     if (!name) FAIL(REMO_ERR_ARG, "remo_set_option: NULL name");

@@ -574,6 +574,10 @@ int spmm_variant() {
   return v;
 }
 
+// even (the SpMM gathers two right-hand sides per 16-byte load); the extra column of an odd count has b = 0
+int solver_stride(int nrhs) { return (nrhs > 1 && spmm_variant() >= 4) ? ((nrhs + 1) & ~1) : nrhs; }
+int spmm_blocks(Ctx* c, int ks) { return spmm_grid(c, ks); }
+
 void launch_spmm(Ctx* c, const double* P, double* Q, int nrhs) {
   const int kp = kp_for(nrhs);
   const int grid = c->num_sms * 8;
@@ -644,7 +648,7 @@ void rhs_point_sources(Ctx* c, int nrhs, const int64_t* src_ptr, const double* s
   cudaStream_t st = c->stream;
   // row stride of the vector blocks: even (the SpMM gathers two right-hand sides per 16-byte load); the extra column
   // of an odd count has b = 0 and is frozen from the first iteration
-  const int ks = (nrhs > 1 && spmm_variant() >= 4) ? ((nrhs + 1) & ~1) : nrhs;
+  const int ks = solver_stride(nrhs);
   alloc_solver_state(c, ks);
   c->nrhs_user = nrhs;
   std::vector<int64_t> hp(nrhs + 1);

@@ -255,3 +255,27 @@ def test_block_sizes_match_oracle(ctx, nrhs):
     np.testing.assert_allclose(got, want, rtol=1e-6)
     with pytest.raises(_cabi.RemoError):
         ctx.solution(nrhs)  # the padding column of an odd width is not addressable
+
+
+@pytest.mark.parametrize("dim,order", [(3, 2), (3, 3), (2, 3)])
+def test_spmm_kernels_against_scipy(ctx, dim, order):
+    """Every SpMM kernel the PCG can pick (CSR one-column, SELL generic for strides 2/4/16/32, SELL streaming for 5..8
+    right-hand sides) against the exact product with the oracle-checked CSR matrix: Q = A P on free rows, 0 on
+    constrained rows, and the fused per-column dots p.q."""
+    mesh, sigma = (helpers.ball_case() if dim == 3 else helpers.disc_case())[:2]
+    _setup(ctx, mesh, order)
+    ctx.assemble(sigma)
+    rowptr, col, val = ctx.matrix()
+    A = sp.csr_matrix((val, col, rowptr), shape=(ctx.ndof, ctx.ndof))
+    con = ctx.dirichlet().astype(bool)
+    absA = abs(A)
+    rng = np.random.default_rng(5)
+    for k in (1, 2, 3, 4, 5, 6, 7, 8, 9, 16, 17, 32):
+        P = rng.standard_normal((ctx.ndof, k))
+        Q, pq = ctx.spmm_apply(P)
+        ref = A @ P
+        ref[con] = 0.0
+        scale = absA @ abs(P) + 1e-300
+        assert np.max(abs(Q - ref) / scale) <= 1e-14 * 8, (k, np.max(abs(Q - ref) / scale))
+        dots = (P * ref).sum(0)
+        assert np.max(abs(pq - dots) / (abs(P * ref).sum(0))) <= 1e-13, k
