@@ -57,3 +57,20 @@ def disc_case(h_electrode=0.03, h_axis=0.15, h_borehole=0.25, grading=0.6, tools
     sigma = [1 / 1.0, 1 / 10.0, 1 / 5.0, 1 / 100.0, 1 / 10.0]
     flat = planner.flatten_task(task, params, three_d=False)
     return mesh, sigma, flat, params
+
+
+def star_case(nsphere=260, seed=3):
+    """One central vertex surrounded by points on a sphere: the Delaunay mesh has ~2 * nsphere tets that all share the
+    centre, so its matrix row has thousands of candidate columns (the whole-CTA path of the CSR pattern builder)."""
+    from scipy.spatial import Delaunay
+
+    rng = np.random.default_rng(seed)
+    v = rng.standard_normal((nsphere, 3))
+    v /= np.linalg.norm(v, axis=1)[:, None]
+    pts = np.vstack([np.zeros((1, 3)), v])
+    elems = Delaunay(pts).simplices.astype(np.int32)
+    # positive orientation is not required by the path (|det| is used), vertex order is sorted on the device
+    bf = meshgen.boundary_facets(elems)
+    bc = np.full(bf.shape[0], 2, dtype=np.int32)
+    mat = (pts[elems].mean(axis=1)[:, 2] > 0).astype(np.int32)
+    return Mesh(pts, elems, mat, bf, bc, ["natural", "dirichlet_boundary"]), [1.0, 0.1]

@@ -279,3 +279,27 @@ def test_spmm_kernels_against_scipy(ctx, dim, order):
         assert np.max(abs(Q - ref) / scale) <= 1e-14 * 8, (k, np.max(abs(Q - ref) / scale))
         dots = (P * ref).sum(0)
         assert np.max(abs(pq - dots) / (abs(P * ref).sum(0))) <= 1e-13, k
+
+
+@pytest.mark.parametrize("order", [2, 3])
+def test_pattern_of_a_high_valence_vertex(ctx, order):
+    """A vertex shared by ~500 tets: its row has > 2048 candidate columns, which takes the whole-CTA branch of the
+    pattern builder; numbering, pattern and values must still match the oracle exactly."""
+    mesh, sigma = helpers.star_case()
+    deg = np.bincount(mesh.elems.ravel()).max()
+    assert deg * (10 if order == 2 else 20) > 2048
+    _setup(ctx, mesh, order)
+    space = fo.Space(mesh.nv, mesh.elems, order, 3)
+    A = fo.assemble(mesh.points, space, sigma, mesh.mat)
+    rowptr, col, _ = ctx.matrix(values=False)
+    np.testing.assert_array_equal(rowptr, A.indptr)
+    np.testing.assert_array_equal(col, A.indices)
+    if np.diff(A.indptr).max() > 2600:
+        # documented limit of the numeric phase: the shared-memory row buffer of k_assemble_rows holds 8 rows at a time;
+        # a 3600-entry row (order 3, 516 tets around one vertex) must fail loudly, not silently
+        with pytest.raises(_cabi.RemoError, match="row buffer"):
+            ctx.assemble(sigma)
+        return
+    ctx.assemble(sigma)
+    val = ctx.matrix()[2]
+    assert np.linalg.norm(val - A.data) / np.linalg.norm(A.data) <= 1e-12

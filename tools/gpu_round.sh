@@ -1,6 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log; tail -3 gpurun_out/smoke.log
-python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_default.err
-python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
-cat gpurun_out/bench_ref.json | cut -c1-600
+timeout 1000 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+python bench.py --steps 4 --warmup 2 --no-cpu-baseline --contexts 1 > gpurun_out/bench_5M_pat1.json 2> gpurun_out/bench_5M_pat1.err
+python bench.py --steps 4 --warmup 2 --no-cpu-baseline > gpurun_out/bench_5M_pat2.json 2> gpurun_out/bench_5M_pat2.err
+python -c "
+import json
+for f in ('pat1','pat2'):
+    d=json.load(open('gpurun_out/bench_5M_%s.json'%f)); print(f, d['value'], d['ms_per_step'], d['config']['stage_ms_one_context_alone'])"
