@@ -37,6 +37,7 @@ TOOLS = ["A2.0M0.5N", "N0.5M2.0A", "B5.7A0.4M", "M4.0A0.5B"]  # SURVEY 8d, confi
 SIGMA = [1 / 1.0, 1 / 10.0, 1 / 100.0, 1 / 10.0, 1 / 2.0]       # mud, 10/100/10 ohm-m beds, inclusion
 SIZES = {
     # name: (h_electrode, h_axis, grading, h_max)  -> dofs at order 2
+    "20M": (0.006, 0.013, 0.075, 3.0),   # config C5: ~2.6 M vertices, ~20 M dofs
     "5M": (0.008, 0.0222, 0.125, 4.0),
     "1M": (0.01, 0.04, 0.19, 5.0),
     "200k": (0.03, 0.1, 0.33, 6.0),
@@ -59,7 +60,7 @@ def make_mesh(size, task, log=lambda *a: None):
 
     he, ha, g, hm = SIZES[size]
     key = hashlib.sha1(repr((size, he, ha, g, hm, task[1][0].tolist(), 3)).encode()).hexdigest()[:12]
-    path = os.path.join(tempfile.gettempdir(), "remo3d_bench_mesh_%s.npz" % key)
+    path = os.path.join(os.environ.get("REMO_MESH_CACHE", tempfile.gettempdir()), "remo3d_bench_mesh_%s.npz" % key)
     if os.path.exists(path):
         z = np.load(path)
         return {k: z[k] for k in z.files}

@@ -451,7 +451,7 @@ void sell_build(Ctx* c) {
     // 4.8 M dofs) is larger than the L2 -- measured 1.01 ms with 42 slices per warp, 0.84 ms with 11..16.
     const int spw = std::max(1, sell_env("REMO_SELL_SPW", 14));
     const int64_t want = (nslices + 8 * spw - 1) / (8 * spw);
-    c->sell_sgrid = (int)std::min<int64_t>(std::max<int64_t>(want, c->num_sms * 4), (int64_t)c->num_sms * 64);
+    c->sell_sgrid = (int)std::min<int64_t>(std::max<int64_t>(want, c->num_sms * 4), (int64_t)c->num_sms * 192);
     const int nw = c->sell_sgrid * 8;
     c->sell_wpart.ensure(nw + 1, st);
     LAUNCH(c, k_sell_partition, grid_for(nw + 1, TB), TB, 0, c->sell_ptr.p, nslices, nw, c->sell_wpart.p);

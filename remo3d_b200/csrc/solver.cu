@@ -558,7 +558,7 @@ void alloc_solver_state(Ctx* c, int nrhs) {
   c->pstride = (spmm_variant() >= 5 && nrhs >= 2 && (nrhs & 1) == 0) ? sell_pstride(nrhs) : nrhs;
   c->P.ensure((size_t)c->ndof * c->pstride, st);
   if (c->pstride != nrhs) CK(cudaMemsetAsync(c->P.p, 0, (size_t)c->ndof * c->pstride * sizeof(double), st));
-  c->partial.ensure((size_t)std::max(vec_grid(c, nrhs), c->num_sms * 64) * 2 * KMAX, st);  // room for any SpMM grid (sell.cu caps its own)
+  c->partial.ensure((size_t)std::max(vec_grid(c, nrhs), c->num_sms * 192) * 2 * KMAX, st);  // room for any SpMM grid (sell.cu caps its own)
   CK(cudaMemsetAsync(c->partial.p, 0, c->partial.n * sizeof(double), st));
   c->scal.ensure(S_NSLOT * KMAX, st);
   c->iters_d.ensure(KMAX, st);

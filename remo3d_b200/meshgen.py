@@ -72,11 +72,21 @@ def boundary_facets(elems, return_owner=False):
     """Faces that belong to exactly one tet (triangles) / edges of exactly one triangle."""
     d1 = elems.shape[1]
     nv = int(elems.max()) + 1
-    if d1 == 4 and nv >= (1 << 21):
-        raise ValueError("boundary_facets: more than 2^21 vertices not supported by the host mesher")
     faces = np.concatenate([np.delete(elems, i, axis=1) for i in range(d1)], axis=0)
-    _, idx, cnt = np.unique(_facet_keys(faces, nv), return_index=True, return_counts=True)
-    sel = idx[cnt == 1]
+    if d1 == 4 and nv >= (1 << 21):
+        # three vertex numbers no longer fit one int64 key: sort the sorted triples lexicographically instead
+        f = np.sort(faces.astype(np.int64), axis=1)
+        key2 = f[:, 0] * nv + f[:, 1]
+        order = np.lexsort((f[:, 2], key2))
+        k2, k3 = key2[order], f[order, 2]
+        new = np.ones(order.shape[0], dtype=bool)
+        new[1:] = (k2[1:] != k2[:-1]) | (k3[1:] != k3[:-1])
+        starts = np.flatnonzero(new)
+        cnt = np.diff(np.r_[starts, order.shape[0]])
+        sel = np.sort(order[starts[cnt == 1]])
+    else:
+        _, idx, cnt = np.unique(_facet_keys(faces, nv), return_index=True, return_counts=True)
+        sel = idx[cnt == 1]
     if return_owner:
         return faces[sel].astype(np.int32), sel % elems.shape[0]
     return faces[sel].astype(np.int32)

@@ -1,9 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1000 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python bench.py --steps 4 --warmup 2 --no-cpu-baseline --contexts 1 > gpurun_out/bench_5M_pat1.json 2> gpurun_out/bench_5M_pat1.err
-python bench.py --steps 4 --warmup 2 --no-cpu-baseline > gpurun_out/bench_5M_pat2.json 2> gpurun_out/bench_5M_pat2.err
+export REMO_MESH_CACHE=$PWD/.meshcache
+timeout 900 python bench.py --size 20M --steps 2 --warmup 1 --no-cpu-baseline --maxit 5000 > gpurun_out/bench_20M.json 2> gpurun_out/bench_20M.err; echo rc=$?
 python -c "
 import json
-for f in ('pat1','pat2'):
-    d=json.load(open('gpurun_out/bench_5M_%s.json'%f)); print(f, d['value'], d['ms_per_step'], d['config']['stage_ms_one_context_alone'])"
+d=json.load(open('gpurun_out/bench_20M.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['ndof'], d['config']['nnz'], d['config']['iterations'], d['config']['stage_ms_one_context_alone'], d['roofline']['frac'], d['roofline']['avg_launch_ms'])"
+nvidia-smi --query-gpu=memory.used --format=csv,noheader
