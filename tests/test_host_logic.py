@@ -154,3 +154,28 @@ def test_densify_borehole():
     np.testing.assert_allclose(np.interp(0.6, d[:, 0], d[:, 1]), 0.15)
     same = model_io.densify_borehole(b[:2])
     assert same is b[:2] or np.array_equal(same, b[:2])
+
+
+def test_save_results_is_byte_compatible_with_the_reference_output(tmp_path):
+    """`Results_<n>.txt` (remo3d.py:957-990): feeding the reference's own committed logs back through save_results must
+    reproduce its file byte for byte (header, tab separation, %.4f), and logs on a different depth grid go to a second
+    file."""
+    import glob
+    import os
+
+    from remo3d_b200 import Model
+
+    golden = os.path.join(os.path.dirname(__file__), "golden", "example_01", "Results_1.txt")
+    lines = open(golden).read().splitlines()
+    names = lines[0].split("\t")[1:]
+    table = np.loadtxt(golden, skiprows=2)
+    model = Model(names)
+    model.logs = {n: np.column_stack([table[:, 0], table[:, 1 + i]]) for i, n in enumerate(names)}
+    model.logs["EXTRA"] = np.column_stack([table[::2, 0], table[::2, 1]])
+    sub = model.save_results(str(tmp_path))
+    files = sorted(glob.glob(os.path.join(sub, "Results_*.txt")))
+    assert [os.path.basename(f) for f in files] == ["Results_1.txt", "Results_2.txt"]
+    assert open(files[0], "rb").read() == open(golden, "rb").read()
+    second = open(files[1]).read().splitlines()
+    assert second[0] == "DEPTH\tEXTRA" and second[1] == "M\tOHMM" and len(second) == 2 + table[::2].shape[0]
+    assert model.save_results(None) is None
