@@ -26,6 +26,26 @@ __global__ void __launch_bounds__(TB) k_ldg(const int32_t* __restrict__ idx, con
   if (a + b == 1.2345) out[0] = a;
 }
 
+// mode 3: 256-bit loads (ld.global.v4.f64, sm_100+), 2 lanes per row
+__global__ void __launch_bounds__(TB) k_ldg256(const int32_t* __restrict__ idx, const double* __restrict__ P, int64_t nper, double* out) {
+  const int l = threadIdx.x & 1, grp = threadIdx.x >> 1;
+  const int32_t* my = idx + (int64_t)blockIdx.x * nper;
+  double a = 0, b = 0;
+  constexpr int G = TB / 2;
+  for (int64_t i = grp; i + 3 * G < nper; i += 4 * G) {
+    const int32_t c0 = my[i], c1 = my[i + G], c2 = my[i + 2 * G], c3 = my[i + 3 * G];
+    double x[4][4];
+    const double* p0 = P + (int64_t)c0 * 8 + l * 4; const double* p1 = P + (int64_t)c1 * 8 + l * 4;
+    const double* p2 = P + (int64_t)c2 * 8 + l * 4; const double* p3 = P + (int64_t)c3 * 8 + l * 4;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x[0][0]), "=d"(x[0][1]), "=d"(x[0][2]), "=d"(x[0][3]) : "l"(p0));
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x[1][0]), "=d"(x[1][1]), "=d"(x[1][2]), "=d"(x[1][3]) : "l"(p1));
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x[2][0]), "=d"(x[2][1]), "=d"(x[2][2]), "=d"(x[2][3]) : "l"(p2));
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x[3][0]), "=d"(x[3][1]), "=d"(x[3][2]), "=d"(x[3][3]) : "l"(p3));
+    for (int q = 0; q < 4; q++) { a += x[q][0] + x[q][2]; b += x[q][1] + x[q][3]; }
+  }
+  if (a + b == 1.2345) out[0] = a;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <int STAGES, int RPS>  // rows per stage
@@ -130,6 +150,7 @@ int main(int argc, char** argv) {
       printf("cps=%d %-28s %.3f ms  %.2f cyc/row/SM  %.0f GB/s\n", cps, name, ms, cyc / (nper * cps), (double)grid * nper * ROWB / ms / 1e6);
     };
     time("ldg128 4 lanes/row", [&] { k_ldg<<<grid, TB>>>(idx, (const double2*)P, nper, out); });
+    time("ldg256 2 lanes/row", [&] { k_ldg256<<<grid, TB>>>(idx, (const double*)P, nper, out); });
     {
       constexpr int ST = 4, RPS = 256;
       CK(cudaFuncSetAttribute(k_bulk<ST, RPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST * RPS * ROWB));
