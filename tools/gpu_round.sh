@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-export REMO_MESH_CACHE=$PWD/.meshcache
-timeout 900 python bench.py --size 20M --steps 2 --warmup 1 --no-cpu-baseline --maxit 5000 > gpurun_out/bench_20M.json 2> gpurun_out/bench_20M.err; echo rc=$?
-python -c "
-import json
-d=json.load(open('gpurun_out/bench_20M.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['ndof'], d['config']['nnz'], d['config']['iterations'], d['config']['stage_ms_one_context_alone'], d['roofline']['frac'], d['roofline']['avg_launch_ms'])"
-nvidia-smi --query-gpu=memory.used --format=csv,noheader
+: > gpurun_out/sweep10.log
+run() { echo "$*" >> gpurun_out/sweep10.log; env "$@" timeout 300 python tools/spmm_probe.py --ks 5,8 2>&1 | grep "^k=\|rror" >> gpurun_out/sweep10.log; }
+for w in 0 2 3 4; do run REMO_SELL_WIDE=$w REMO_PROBE_SIZE=5M; done
+for w in 0 3; do run REMO_SELL_WIDE=$w REMO_PROBE_SIZE=1M; done
+cat gpurun_out/sweep10.log
+REMO_SELL_WIDE=3 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "spmm or block or rhs" 2>&1 | tail -3
