@@ -101,6 +101,9 @@ int remo_ctx_destroy(void* vctx) {
   c->dinv.release(s); amg_release(c);
   c->F.release(s); c->X.release(s); c->R.release(s); c->Z.release(s); c->P.release(s); c->Q.release(s);
   c->partial.release(s); c->scal.release(s); c->iters_d.release(s); c->tmp.release(s);
+  c->sell_ptr.release(s); c->sell_col.release(s); c->sell_val.release(s); c->sell_row.release(s); c->sell_part.release(s);
+  c->sell_wpart.release(s); c->bbox.release(s);
+  for (auto& b : c->scr) b.release(s);
   cudaStreamSynchronize(s);
   for (int i = 0; i < REMO_NSTAGE; i++) { cudaEventDestroy(c->ev0[i]); cudaEventDestroy(c->ev1[i]); }
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
