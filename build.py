@@ -6,7 +6,7 @@ import sys
 ROOT = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(ROOT, "remo3d_b200", "csrc")
 LIB = os.path.join(ROOT, "remo3d_b200", "libremo3d_b200.so")
-SOURCES = ["symbolic.cu", "assemble.cu", "solver.cu", "sell.cu", "amg.cu", "cabi.cu"]
+SOURCES = ["symbolic.cu", "assemble.cu", "solver.cu", "sell.cu", "ebe.cu", "amg.cu", "cabi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Wno-deprecated-declarations", "-diag-suppress", "177"]
 

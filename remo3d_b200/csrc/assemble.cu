@@ -236,6 +236,7 @@ void assemble(Ctx* c, int nmat, const double* sigma) {
   assemble_kernels_only(c);
   c->have_matrix = true;
   c->have_sell = false;
+  c->have_ebe = false;
   c->pkind = -1;
   c->have_solution = false;
 }

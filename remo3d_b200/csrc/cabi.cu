@@ -103,6 +103,7 @@ int remo_ctx_destroy(void* vctx) {
   c->partial.release(s); c->scal.release(s); c->iters_d.release(s); c->tmp.release(s);
   c->sell_ptr.release(s); c->sell_col.release(s); c->sell_val.release(s); c->sell_row.release(s); c->sell_part.release(s);
   c->sell_wpart.release(s); c->bbox.release(s);
+  c->ebe_uoff.release(s); c->ebe_udof.release(s); c->ebe_lidx.release(s); c->ebe_lpos.release(s); c->ebe_incptr.release(s); c->ebe_gm.release(s);
   for (auto& b : c->scr) b.release(s);
   cudaStreamSynchronize(s);
   for (int i = 0; i < REMO_NSTAGE; i++) { cudaEventDestroy(c->ev0[i]); cudaEventDestroy(c->ev1[i]); }
@@ -138,7 +139,7 @@ int remo_mesh_set(void* vctx, int dim, int64_t nv, const double* xyz, int64_t nt
     if (naxis < 0 || (naxis > 0 && !axis_vertices)) FAIL(REMO_ERR_ARG, "remo_mesh_set: axis array missing");
     StageTimer timer(c, ST_MESH);
     cudaStream_t st = c->stream;
-    c->have_mesh = c->have_bbox = c->have_space = c->have_matrix = c->have_sell = c->have_rhs = c->have_solution = false;
+    c->have_mesh = c->have_bbox = c->have_space = c->have_matrix = c->have_sell = c->have_ebe = c->have_rhs = c->have_solution = false;
     c->pkind = -1;
     c->dim = dim; c->nv = nv; c->nt = nt; c->nb = nb; c->naxis = naxis;
     c->xyz.ensure(nv * dim, st); c->elems.ensure(nt * (dim + 1), st); c->mat.ensure(nt, st);
@@ -355,6 +356,7 @@ int remo_set_option(void* vctx, const char* name, double value) {
     const std::string n(name);
     if (n == "amg_alpha") c->amg_alpha = value;
     else if (n == "amg_sweeps") c->amg_sweeps = std::max(1, (int)value);
+    else if (n == "spmm_ebe") { c->ebe_on = value != 0.0 ? 1 : 0; c->have_ebe = false; c->pkind = -1; }
     else if (n == "amg_omega_scale") { c->amg_omega_scale = value; c->pkind = -1; }
     else FAIL(REMO_ERR_ARG, "remo_set_option: unknown option '%s'", name);
     return REMO_OK;

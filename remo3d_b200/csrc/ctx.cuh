@@ -111,6 +111,19 @@ struct Ctx {
   int64_t sell_chunks = 0, sell_slots = 0;
   bool have_sell = false;
 
+  // ---- element-wise product for order-2 tets (ebe.cu): batches of 256 Morton-ordered tets
+  DBuf<int64_t> ebe_uoff;     // nb+1: first distinct dof of every batch
+  DBuf<int32_t> ebe_udof;     // distinct dofs of every batch, bit 31 = constrained
+  DBuf<uint16_t> ebe_lidx;    // nb x 10 x 256: (slot, tet) -> position in the batch's dof list
+  DBuf<uint16_t> ebe_lpos;    // nb x 10 x 256: (slot, tet) -> position in the batch's dof-major scratch
+  DBuf<uint16_t> ebe_incptr;  // per batch U+1 first scratch positions of its dofs (batch b starts at ebe_uoff[b] + b)
+  DBuf<double> ebe_gm;        // nb x 10 x 256: metric numbers in batch order
+  int64_t ebe_nb = 0;
+  int ebe_umax = 0;
+  int ebe_occ[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // resident CTAs per SM by right-hand-side count
+  bool have_ebe = false;
+  int ebe_on = -1;  // remo_set_option("spmm_ebe"): 0 / 1, -1 = the REMO_SPMM_EBE environment default (on)
+
   // ---- numeric
   DBuf<double> gm;     // nt x npair: sigma |K| grad l_i . grad l_j
   DBuf<double> sigma;  // nmat
@@ -218,6 +231,12 @@ int sell_pstride(int ks);
 void sell_build(Ctx* c);
 int sell_grid(const Ctx* c);
 void launch_spmm_sell(Ctx* c, const double* P, double* Q, int ks, int pstride);
+// ebe.cu
+bool ebe_eligible(const Ctx* c);
+bool ebe_usable(const Ctx* c, int nr);
+void ebe_build(Ctx* c);
+int ebe_grid(const Ctx* c, int nr);
+void launch_spmm_ebe(Ctx* c, const double* P, int pstride, double* Q, int ks, int nr);
 // amg.cu
 void amg_setup(Ctx* c);
 void amg_apply(Ctx* c, const double* R, double* Z, int nrhs);

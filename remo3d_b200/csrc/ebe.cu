@@ -1,0 +1,376 @@
+// Element-wise multi-right-hand-side product Q = A P (+ fused p.q) for order-2 tetrahedra: the PCG "SpMM" without the
+// assembled matrix.
+//
+// Why.  The CSR / SELL SpMM gathers one 64-byte row of P per matrix entry (136.9 M gathers at 4.8 M dofs) and is bound
+// by the latency x concurrency of those gathers at ~36 % of the HBM roofline (profiles/r01_notes.md).  The same product
+// taken element by element needs 10 dofs per tet -- 38 M (tet, dof) incidences instead of 137 M entries -- and the
+// element matrix need not be read at all: for the hierarchical P2 basis (vertex l_i, edge l_a l_b; oracle
+// local_basis, assemble.cu tensors) it is a closed form of the 10 metric numbers  S_ij = sigma |K| grad l_i . grad l_j
+// that k_geom_tet already leaves in c->gm:
+//     grad u = sum_j c_j(l) grad l_j,   c_j = x_j + sum_{b != j} x_{jb} l_b         (linear in the barycentrics)
+//     y_i    = sum_j S_ij mean(c_j)                    mean(c_j)     = x_j + s_j / 4,          s_j = sum_b x_{jb}
+//     y_ab   = sum_j S_bj mean(l_a c_j) + S_aj mean(l_b c_j),   mean(l_a c_j) = x_j / 4 + (s_j + x_{ja}) / 20
+// (~150 flops per tet and right-hand side; checked against the exact tensors in tests/test_oracle.py).
+//
+// Layout.  Tets are taken in Morton order of their centroid and cut into batches of 256 (one CTA pass, one tet per
+// thread).  Per batch, built once per matrix by k_ebe_batch (block radix sort of the 2560 (dof, slot) pairs):
+//   udof   [U]        the distinct dofs of the batch (U ~ 620), bit 31 = constrained
+//   lidx   [10][256]  slot -> position in udof (16 bit), coalesced per slot
+//   lpos   [10][256]  slot -> position of its result in the dof-major (sorted) scratch; incptr [U + 1] = first
+//                     position of every dof: the transpose map
+//   gmb    [10][256]  the metric numbers in batch order, coalesced per number
+// The kernel stages the U rows of P in shared memory with cp.async (one gather per DISTINCT dof of a batch: 8.2 M
+// instead of 137 M), then per right-hand side: every thread applies its element to the staged values and parks the 10
+// results at their dof-major positions of a scratch; one thread per dof adds its consecutive entries (fixed order, no
+// shared-memory atomics), takes its p.q share and overwrites the staged value in place.  After the last pass one fp64
+// RED per (dof, right-hand side) adds the batch's share to Q, which is zeroed first.  Sums across batches are
+// RED-ordered, so Q is reproducible to rounding only.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "space_view.cuh"
+
+namespace {
+
+constexpr int TPB = 256;  // tets per batch = threads per CTA
+constexpr int NLD = 10;   // local dofs of the P2 tet
+constexpr int KMAX = REMO_MAX_RHS;
+constexpr int EBE_MAX_RHS = 8;
+constexpr uint32_t SENT = 0xffffffffu;
+
+__global__ void k_tet_morton(const int32_t* __restrict__ sv, const double* __restrict__ xyz, const double* __restrict__ lohi,
+                             int64_t nt, uint64_t* __restrict__ code, int32_t* __restrict__ idx) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= nt) return;
+  const int4 v = reinterpret_cast<const int4*>(sv)[t];
+  uint64_t c = 0;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const double x = 0.25 * (xyz[3 * (int64_t)v.x + d] + xyz[3 * (int64_t)v.y + d] + xyz[3 * (int64_t)v.z + d] + xyz[3 * (int64_t)v.w + d]);
+    const double ext = lohi[3 + d] - lohi[d];
+    const double u = ext > 0 ? (x - lohi[d]) / ext : 0.0;
+    const uint64_t q = (uint64_t)fmin(fmax(u * 2097151.0, 0.0), 2097151.0);
+    c |= spread21s(q) << d;
+  }
+  code[t] = c;
+  idx[t] = (int32_t)t;
+}
+
+// One CTA per batch.  FILL = false: count the distinct dofs; true: write the batch tables at the offsets uoff[].
+template <bool FILL>
+__global__ void __launch_bounds__(TPB) k_ebe_batch(SpaceView s, const int32_t* __restrict__ tperm,
+                                                   const uint8_t* __restrict__ constrained, int64_t* __restrict__ ucount,
+                                                   int* __restrict__ umax, const int64_t* __restrict__ uoff,
+                                                   int32_t* __restrict__ udof, uint16_t* __restrict__ lidx,
+                                                   uint16_t* __restrict__ lpos, uint16_t* __restrict__ incptr) {
+  using Sort = cub::BlockRadixSort<uint32_t, TPB, NLD, uint16_t>;
+  using Scan = cub::BlockScan<int, TPB>;
+  __shared__ union Tmp {
+    typename Sort::TempStorage sort;
+    typename Scan::TempStorage scan;
+  } tmp;
+  __shared__ uint32_t skey[TPB * NLD];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int64_t ti = (int64_t)b * TPB + tid;
+  uint32_t key[NLD];
+  uint16_t val[NLD];
+  if (ti < s.nt) {
+    const int64_t t = tperm[ti];
+#pragma unroll
+    for (int k = 0; k < 4; k++) key[k] = (uint32_t)s.sv[t * 4 + k];
+#pragma unroll
+    for (int k = 0; k < 6; k++) key[4 + k] = (uint32_t)(s.edge_base + s.elem_edges[t * 6 + k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < NLD; k++) key[k] = SENT;
+  }
+#pragma unroll
+  for (int k = 0; k < NLD; k++) val[k] = (uint16_t)(k * TPB + tid);
+  Sort(tmp.sort).Sort(key, val);  // blocked arrangement: thread i holds the sorted positions 10 i .. 10 i + 9
+#pragma unroll
+  for (int k = 0; k < NLD; k++) skey[tid * NLD + k] = key[k];
+  __syncthreads();
+  bool head[NLD];
+  int heads = 0;
+#pragma unroll
+  for (int k = 0; k < NLD; k++) {
+    const int pos = tid * NLD + k;
+    head[k] = key[k] != SENT && (pos == 0 || skey[pos - 1] != key[k]);
+    heads += head[k] ? 1 : 0;
+  }
+  int base = 0, total = 0;
+  Scan(tmp.scan).ExclusiveSum(heads, base, total);
+  if (!FILL) {
+    if (tid == 0) {
+      ucount[b] = total;
+      atomicMax(umax, total);
+    }
+    return;
+  }
+  const int64_t u0 = uoff[b];
+  const int64_t bo = (int64_t)b * (TPB * NLD);
+  int cnt = 0;
+#pragma unroll
+  for (int k = 0; k < NLD; k++) {
+    const int pos = tid * NLD + k;
+    if (head[k]) {
+      const int rank = base + cnt;
+      cnt++;
+      udof[u0 + rank] = (int32_t)(key[k] | (constrained[key[k]] ? 0x80000000u : 0u));
+      incptr[u0 + b + rank] = (uint16_t)pos;
+    }
+    const int rank = base + cnt - 1;  // distinct dofs at positions <= pos, minus one
+    lidx[bo + val[k]] = (uint16_t)(key[k] != SENT ? rank : 0);
+    lpos[bo + val[k]] = (uint16_t)pos;  // padding tets sort behind every real entry
+  }
+  if (tid == 0) {
+    const int64_t left = s.nt - (int64_t)b * TPB;
+    incptr[u0 + b + total] = (uint16_t)((left < TPB ? left : TPB) * NLD);
+  }
+}
+
+__global__ void k_ebe_gm(const double* __restrict__ gm, const int32_t* __restrict__ tperm, int64_t nt, int64_t nb,
+                         double* __restrict__ gmb) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // i = b * TPB + tet
+  if (i >= nb * TPB) return;
+  const int64_t b = i / TPB, l = i - b * TPB;
+  const bool in = i < nt;
+  const double* g = gm + (in ? (int64_t)tperm[i] : 0) * NLD;
+#pragma unroll
+  for (int m = 0; m < NLD; m++) gmb[(b * NLD + m) * TPB + l] = in ? g[m] : 0.0;
+}
+
+__global__ void k_ebe_offsets_in(const int64_t* __restrict__ ucount, int64_t nb, int64_t* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i <= nb) out[i] = i < nb ? ucount[i] : 0;
+}
+
+// y = K_e x for one P2 tet from its 10 metric numbers (pairs (0,0) (0,1) (0,2) (0,3) (1,1) (1,2) (1,3) (2,2) (2,3) (3,3);
+// local dofs: vertices 0..3, then the edges (0,1) (0,2) (0,3) (1,2) (1,3) (2,3) of the sorted tet)
+__device__ __forceinline__ void p2_apply(const double (&g)[NLD], const double (&x)[NLD], double (&y)[NLD]) {
+  const double S[4][4] = {{g[0], g[1], g[2], g[3]}, {g[1], g[4], g[5], g[6]}, {g[2], g[5], g[7], g[8]}, {g[3], g[6], g[8], g[9]}};
+  // xe[j][a] = edge value between the local vertices j and a (0 on the diagonal)
+  const double xe[4][4] = {{0.0, x[4], x[5], x[6]}, {x[4], 0.0, x[7], x[8]}, {x[5], x[7], 0.0, x[9]}, {x[6], x[8], x[9], 0.0}};
+  double d0[4], bs[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const double sj = (xe[j][0] + xe[j][1]) + (xe[j][2] + xe[j][3]);
+    d0[j] = fma(0.25, sj, x[j]);
+    bs[j] = fma(0.05, sj, 0.25 * x[j]);
+  }
+  double B[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    y[i] = fma(S[i][0], d0[0], fma(S[i][1], d0[1], fma(S[i][2], d0[2], S[i][3] * d0[3])));
+    B[i] = fma(S[i][0], bs[0], fma(S[i][1], bs[1], fma(S[i][2], bs[2], S[i][3] * bs[3])));
+  }
+  // V[b][a] = sum_j S_bj xe[j][a]
+  double V[4][4];
+#pragma unroll
+  for (int bb = 0; bb < 4; bb++)
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      if (a == bb) { V[bb][a] = 0.0; continue; }
+      double v = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (j != a) v = fma(S[bb][j], xe[j][a], v);
+      V[bb][a] = v;
+    }
+  constexpr int EA[6] = {0, 0, 0, 1, 1, 2}, EB[6] = {1, 2, 3, 2, 3, 3};
+#pragma unroll
+  for (int e = 0; e < 6; e++) y[4 + e] = (B[EA[e]] + B[EB[e]]) + 0.05 * (V[EB[e]][EA[e]] + V[EA[e]][EB[e]]);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(TPB, 3) k_spmm_ebe(int nb, const int64_t* __restrict__ uoff, const int32_t* __restrict__ udof,
+                                                     const uint16_t* __restrict__ lidx, const uint16_t* __restrict__ lpos,
+                                                     const uint16_t* __restrict__ incptr, const double* __restrict__ gmb,
+                                                     const double* __restrict__ P, int pstride, double* __restrict__ Q, int ks,
+                                                     int nr, int xst, int umax, double* __restrict__ partial) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // xs: umax x xst staged rows of P (xst odd: random rows spread over the banks); column r is overwritten in place by
+  // the batch's share of Q once pass r no longer needs it.  scr: the element results of the current pass in SORTED
+  // (dof-major) order.  Offsets into xs / scr are BYTE offsets (< 64 K, kept as 16-bit pairs).
+  unsigned char* xs = smem_raw;
+  double* scr = reinterpret_cast<double*>(xs + (size_t)umax * xst * 8);
+  int32_t* sdof = reinterpret_cast<int32_t*>(scr + NLD * TPB);
+  uint16_t* sptr = reinterpret_cast<uint16_t*>(sdof + umax);
+  __shared__ double sdot[TPB / 32][EBE_MAX_RHS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fr = tid & 7;  // staging / flush: 8 lanes per dof row, lane = right-hand side
+  const int xstep = xst * 8;
+  if (tid < (TPB / 32) * EBE_MAX_RHS) (&sdot[0][0])[tid] = 0.0;
+  for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+    const int64_t u0 = uoff[b];
+    const int U = (int)(uoff[b + 1] - u0);
+    for (int i = tid; i < U; i += TPB) sdof[i] = udof[u0 + i];
+    for (int i = tid; i <= U; i += TPB) sptr[i] = incptr[u0 + b + i];
+    __syncthreads();
+    // stage the U rows of P: every copy of the batch is issued before anything waits (cp.async, 8 bytes per lane)
+    if (fr < nr) {
+      const uint32_t dst = smem_u32(xs) + fr * 8;
+      const double* src = P + fr;
+      for (int row = tid >> 3; row < U; row += TPB / 8) {
+        const int64_t dof = sdof[row] & 0x7fffffff;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + row * xstep), "l"(src + dof * pstride) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    uint32_t lxo[NLD / 2], lso[NLD / 2];  // per slot: byte offset of its staged row in xs / of its sorted position in scr
+    double g[NLD];
+#pragma unroll
+    for (int k = 0; k < NLD / 2; k++) {
+      const int64_t o0 = ((int64_t)b * NLD + 2 * k) * TPB + tid, o1 = o0 + TPB;
+      lxo[k] = ((uint32_t)__ldcs(lidx + o0) * xstep) | (((uint32_t)__ldcs(lidx + o1) * xstep) << 16);
+      lso[k] = ((uint32_t)__ldcs(lpos + o0) * 8u) | (((uint32_t)__ldcs(lpos + o1) * 8u) << 16);
+    }
+#pragma unroll
+    for (int k = 0; k < NLD; k++) g[k] = __ldcs(gmb + ((int64_t)b * NLD + k) * TPB + tid);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    for (int r = 0; r < nr; r++) {
+      {
+        double x[NLD], y[NLD];
+        const unsigned char* xr = xs + r * 8;
+#pragma unroll
+        for (int k = 0; k < NLD; k++) x[k] = *reinterpret_cast<const double*>(xr + ((lxo[k >> 1] >> ((k & 1) * 16)) & 0xffffu));
+        p2_apply(g, x, y);
+        unsigned char* sb = reinterpret_cast<unsigned char*>(scr);
+#pragma unroll
+        for (int k = 0; k < NLD; k++) *reinterpret_cast<double*>(sb + ((lso[k >> 1] >> ((k & 1) * 16)) & 0xffffu)) = y[k];
+      }
+      __syncthreads();
+      // per dof: its entries are consecutive in scr; fixed order, no atomics.  Dofs come sorted by number, i.e. the
+      // vertices (20-40 entries) first and together in the first warps, then the edges (~4 entries)
+      double d = 0.0;
+      for (int u = tid; u < U; u += TPB) {
+        const double* e = scr + sptr[u];
+        int n = (int)sptr[u + 1] - (int)sptr[u];
+        double s0 = 0.0, s1 = 0.0;
+        for (; n >= 2; n -= 2, e += 2) {
+          s0 += e[0];
+          s1 += e[1];
+        }
+        if (n) s0 += e[0];
+        s0 += s1;
+        double* px = reinterpret_cast<double*>(xs + u * xstep + r * 8);
+        if (sdof[u] >= 0) d = fma(s0, *px, d);  // p.q: constrained rows do not count (and are not written to Q)
+        *px = s0;
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      if (lane == 0) sdot[warp][r] += d;
+      __syncthreads();  // everybody has read scr: the next pass may overwrite it
+    }
+    // flush the batch's share of Q: one RED per (dof, right-hand side), 8 lanes per dof row
+    if (fr < nr) {
+      for (int row = tid >> 3; row < U; row += TPB / 8) {
+        const int32_t dc = sdof[row];
+        if (dc >= 0) atomicAdd(Q + (int64_t)dc * ks + fr, *reinterpret_cast<const double*>(xs + row * xstep + fr * 8));
+      }
+    }
+    __syncthreads();  // the next batch restages xs / sdof
+  }
+  if (tid < ks) {
+    double t = 0.0;
+    if (tid < nr)
+      for (int w = 0; w < TPB / 32; w++) t += sdot[w][tid];
+    partial[(int64_t)blockIdx.x * KMAX + tid] = t;
+  }
+}
+
+size_t ebe_smem(int umax, int nr) {
+  const int xst = nr | 1;
+  return (size_t)umax * xst * 8 + (size_t)NLD * TPB * 8 + (size_t)umax * 4 + (size_t)(umax + 2) * 2;
+}
+
+}  // namespace
+
+bool ebe_eligible(const Ctx* c) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("REMO_SPMM_EBE");
+    on = e ? atoi(e) : 1;
+  }
+  if (c->ebe_on >= 0 ? c->ebe_on == 0 : on == 0) return false;
+  return c->dim == 3 && c->order == 2 && c->ndof < 0x7fffffff;
+}
+
+bool ebe_usable(const Ctx* c, int nr) { return c->have_ebe && nr >= 1 && nr <= EBE_MAX_RHS && c->ebe_occ[nr] > 0; }
+
+int ebe_grid(const Ctx* c, int nr) { return (int)std::min<int64_t>(c->ebe_nb, (int64_t)c->num_sms * c->ebe_occ[nr]); }
+
+void ebe_build(Ctx* c) {
+  cudaStream_t st = c->stream;
+  const int64_t nt = c->nt, nb = (nt + TPB - 1) / TPB;
+  size_t bytes = 0;
+  // tets in Morton order of their centroid: a batch is a compact blob, consecutive batches are neighbours
+  uint64_t* code = scratch<uint64_t>(c, 0, nt);
+  uint64_t* codes = scratch<uint64_t>(c, 1, nt);
+  int32_t* idx = scratch<int32_t>(c, 2, nt);
+  int32_t* tperm = scratch<int32_t>(c, 3, nt);
+  LAUNCH(c, k_tet_morton, grid_for(nt, TPB), TPB, 0, c->sv.p, c->xyz.p, mesh_bbox(c), nt, code, idx);
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, code, codes, idx, tperm, nt, 0, 63, st));
+  c->tmp.ensure(bytes, st);
+  CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, code, codes, idx, tperm, nt, 0, 63, st));
+  c->launches += 4;
+  // pass 1: distinct dofs per batch -> offsets
+  int64_t* ucount = scratch<int64_t>(c, 4, nb + 1);
+  int64_t* uin = scratch<int64_t>(c, 5, nb + 1);
+  int* umax_d = scratch<int>(c, 6, 1);
+  CK(cudaMemsetAsync(umax_d, 0, sizeof(int), st));
+  SpaceView sview = make_view(c);
+  LAUNCH(c, k_ebe_batch<false>, (unsigned)nb, TPB, 0, sview, tperm, c->constrained.p, ucount, umax_d, nullptr, nullptr, nullptr, nullptr, nullptr);
+  LAUNCH(c, k_ebe_offsets_in, grid_for(nb + 1, TPB), TPB, 0, ucount, nb, uin);
+  c->ebe_uoff.ensure(nb + 1, st);
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, uin, c->ebe_uoff.p, nb + 1, st));
+  c->tmp.ensure(bytes, st);
+  CK(cub::DeviceScan::ExclusiveSum(c->tmp.p, bytes, uin, c->ebe_uoff.p, nb + 1, st));
+  c->launches++;
+  int64_t total = 0;
+  int umax = 0;
+  CK(cudaMemcpyAsync(&total, c->ebe_uoff.p + nb, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&umax, umax_d, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  umax = (umax + 1) & ~1;  // even: the 16-byte alignment of the shared-memory arrays behind xs
+  // pass 2: tables
+  c->ebe_udof.ensure(total, st);
+  c->ebe_incptr.ensure(total + nb + 1, st);
+  c->ebe_lidx.ensure((size_t)nb * TPB * NLD, st);
+  c->ebe_lpos.ensure((size_t)nb * TPB * NLD, st);
+  c->ebe_gm.ensure((size_t)nb * TPB * NLD, st);
+  LAUNCH(c, k_ebe_batch<true>, (unsigned)nb, TPB, 0, sview, tperm, c->constrained.p, nullptr, nullptr, c->ebe_uoff.p, c->ebe_udof.p,
+         c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_incptr.p);
+  LAUNCH(c, k_ebe_gm, grid_for(nb * TPB, TPB), TPB, 0, c->gm.p, tperm, nt, nb, c->ebe_gm.p);
+  c->ebe_nb = nb;
+  c->ebe_umax = umax;
+  // resident CTAs per SM for every right-hand-side count (the shared-memory row stride of xs depends on it)
+  int dev_max = 0;
+  CK(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+  const size_t top = std::min<size_t>(ebe_smem(umax, EBE_MAX_RHS), (size_t)dev_max);
+  CK(cudaFuncSetAttribute(k_spmm_ebe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)top));
+  for (int nr = 1; nr <= EBE_MAX_RHS; nr++) {
+    const size_t sm = ebe_smem(umax, nr);
+    int occ = 0;
+    // the kernel keeps byte offsets into xs as 16-bit numbers
+    if (sm <= (size_t)dev_max && (size_t)umax * (nr | 1) * 8 < 65536) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_ebe, TPB, sm));
+    c->ebe_occ[nr] = occ;  // 0: a batch does not fit (degenerate mesh) -> the SELL / CSR kernels take over
+  }
+  c->have_ebe = true;
+}
+
+void launch_spmm_ebe(Ctx* c, const double* P, int pstride, double* Q, int ks, int nr) {
+  cudaStream_t st = c->stream;
+  CK(cudaMemsetAsync(Q, 0, (size_t)c->ndof * ks * sizeof(double), st));
+  const int xst = nr | 1;
+  const int grid = ebe_grid(c, nr);
+  const size_t sm = ebe_smem(c->ebe_umax, nr);
+  k_spmm_ebe<<<grid, TPB, sm, st>>>((int)c->ebe_nb, c->ebe_uoff.p, c->ebe_udof.p, c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_incptr.p, c->ebe_gm.p,
+                                    P, pstride, Q, ks, nr, xst, c->ebe_umax, c->partial.p);
+  c->launches += 2;
+  CK(cudaGetLastError());
+}

@@ -57,16 +57,6 @@ __global__ void k_sell_keys(const int64_t* __restrict__ rowptr, const int32_t* _
 }
 
 // ---- spatial cluster order of the rows: Morton code of the dof's location (vertex, edge midpoint, face / cell centroid)
-__device__ __forceinline__ uint64_t spread21s(uint64_t v) {
-  v &= 0x1fffffull;
-  v = (v | (v << 32)) & 0x1f00000000ffffull;
-  v = (v | (v << 16)) & 0x1f0000ff0000ffull;
-  v = (v | (v << 8)) & 0x100f00f00f00f00full;
-  v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
-  v = (v | (v << 2)) & 0x1249249249249249ull;
-  return v;
-}
-
 // bounding box of the vertices, two stages: per-block min / max, then one block over the block results
 __global__ void k_bbox_stage(const double* __restrict__ in, int64_t count, int dim, int from_blocks, double* __restrict__ out) {
   // from_blocks == 0: `in` = xyz (count vertices);  1: `in` = count block results [6] -> out[0..2] = min, out[3..5] = max

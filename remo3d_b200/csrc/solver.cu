@@ -535,7 +535,12 @@ int vec_grid(Ctx* c, int ks) {
   if ((ks) & 1) { constexpr int W = 1; CALL; }    \
   else { constexpr int W = 2; CALL; }
 bool use_sell(const Ctx* c, int nrhs, const double* P) { return c->have_sell && c->pstride >= 2 && (nrhs & 1) == 0 && P == c->P.p; }
-int spmm_grid(Ctx* c, int nrhs) { return use_sell(c, nrhs, c->P.p) ? sell_grid(c) : c->num_sms * 8; }
+// element-wise product (ebe.cu): order-2 tets, the PCG's own P block, up to 8 right-hand sides
+bool use_ebe(const Ctx* c, const double* P) { return P == c->P.p && ebe_usable(c, c->nrhs_user); }
+int spmm_grid(Ctx* c, int nrhs) {
+  if (use_ebe(c, c->P.p)) return ebe_grid(c, c->nrhs_user);
+  return use_sell(c, nrhs, c->P.p) ? sell_grid(c) : c->num_sms * 8;
+}
 
 void check_bad(Ctx* c, DBuf<int>& bad, const char* who) {
   int h = 0;
@@ -581,6 +586,10 @@ int spmm_blocks(Ctx* c, int ks) { return spmm_grid(c, ks); }
 void launch_spmm(Ctx* c, const double* P, double* Q, int nrhs) {
   const int kp = kp_for(nrhs);
   const int grid = c->num_sms * 8;
+  if (use_ebe(c, P)) {  // no assembled matrix at all: element by element from the metric numbers (ebe.cu)
+    launch_spmm_ebe(c, P, c->pstride, Q, nrhs, c->nrhs_user);
+    return;
+  }
   if (use_sell(c, nrhs, P)) {  // SELL copy + power-of-two P stride (sell.cu)
     launch_spmm_sell(c, P, Q, nrhs, c->pstride);
     return;
@@ -638,6 +647,7 @@ void precond_setup(Ctx* c, int kind) {
   LAUNCH(c, k_dinv, grid_for(c->ndof, TB), TB, 0, c->rowptr.p, c->col.p, c->val.p, c->constrained.p, c->dinv.p, c->ndof);
   if (kind == REMO_PRECOND_MULTIGRID) amg_setup(c);
   if (spmm_variant() >= 5 && !c->have_sell) sell_build(c);
+  if (ebe_eligible(c) && !c->have_ebe) ebe_build(c);
   c->pkind = kind;
 }
 

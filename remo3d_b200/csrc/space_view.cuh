@@ -54,6 +54,17 @@ __device__ __forceinline__ int64_t find_edge(const SpaceView& s, int32_t a, int3
   return (pos < s.ne && s.edge_keys[pos] == key) ? pos : -1;
 }
 
+// 21 bits -> every third bit (Morton codes of dof / element locations)
+__device__ __forceinline__ uint64_t spread21s(uint64_t v) {
+  v &= 0x1fffffull;
+  v = (v | (v << 32)) & 0x1f00000000ffffull;
+  v = (v | (v << 16)) & 0x1f0000ff0000ffull;
+  v = (v | (v << 8)) & 0x100f00f00f00f00full;
+  v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+  v = (v | (v << 2)) & 0x1249249249249249ull;
+  return v;
+}
+
 #define REMO_SNAP_TOL 1e-9
 
 // Non-zero basis functions at the axis point z (oracle Axis.shape).

@@ -316,7 +316,7 @@ void space_build(Ctx* c, int order) {
   c->nlf = (dim == 3) ? 4 : 1;
   c->npair = nvl * (nvl + 1) / 2;
   c->nld = nvl + c->nle * (order - 1) + (order == 3 ? c->nlf : 0);
-  c->have_space = c->have_matrix = c->have_sell = false;
+  c->have_space = c->have_matrix = c->have_sell = c->have_ebe = false;
   c->pkind = -1;
 
   // 1. sorted element vertices
