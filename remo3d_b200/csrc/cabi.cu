@@ -103,7 +103,7 @@ int remo_ctx_destroy(void* vctx) {
   c->partial.release(s); c->scal.release(s); c->iters_d.release(s); c->tmp.release(s);
   c->sell_ptr.release(s); c->sell_col.release(s); c->sell_val.release(s); c->sell_row.release(s); c->sell_part.release(s);
   c->sell_wpart.release(s); c->bbox.release(s);
-  c->ebe_uoff.release(s); c->ebe_udof.release(s); c->ebe_lidx.release(s); c->ebe_lpos.release(s); c->ebe_incptr.release(s); c->ebe_gm.release(s);
+  c->ebe_uoff.release(s); c->ebe_udof.release(s); c->ebe_lidx.release(s); c->ebe_lpos.release(s); c->ebe_ucnt.release(s); c->ebe_jd.release(s); c->ebe_gm.release(s);
   for (auto& b : c->scr) b.release(s);
   cudaStreamSynchronize(s);
   for (int i = 0; i < REMO_NSTAGE; i++) { cudaEventDestroy(c->ev0[i]); cudaEventDestroy(c->ev1[i]); }

@@ -116,7 +116,8 @@ struct Ctx {
   DBuf<int32_t> ebe_udof;     // distinct dofs of every batch, bit 31 = constrained
   DBuf<uint16_t> ebe_lidx;    // nb x 10 x 256: (slot, tet) -> position in the batch's dof list
   DBuf<uint16_t> ebe_lpos;    // nb x 10 x 256: (slot, tet) -> position in the batch's dof-major scratch
-  DBuf<uint16_t> ebe_incptr;  // per batch U+1 first scratch positions of its dofs (batch b starts at ebe_uoff[b] + b)
+  DBuf<uint16_t> ebe_ucnt;    // entries (incident tets) of every distinct dof inside its batch
+  DBuf<uint16_t> ebe_jd;      // nb x 264: jagged-diagonal offsets of the batch's scratch
   DBuf<double> ebe_gm;        // nb x 10 x 256: metric numbers in batch order
   int64_t ebe_nb = 0;
   int ebe_umax = 0;

@@ -16,12 +16,12 @@
 // thread).  Per batch, built once per matrix by k_ebe_batch (block radix sort of the 2560 (dof, slot) pairs):
 //   udof   [U]        the distinct dofs of the batch (U ~ 620), bit 31 = constrained
 //   lidx   [10][256]  slot -> position in udof (16 bit), coalesced per slot
-//   lpos   [10][256]  slot -> position of its result in the dof-major (sorted) scratch; incptr [U + 1] = first
-//                     position of every dof: the transpose map
+//   lpos   [10][256]  slot -> position of its result in the scratch; the scratch is dof-major in jagged-diagonal
+//                     form (dofs ranked by entry count, entry i of dof u at jd[i] + u), ucnt [U] = entries per dof
 //   gmb    [10][256]  the metric numbers in batch order, coalesced per number
 // The kernel stages the U rows of P in shared memory with cp.async (one gather per DISTINCT dof of a batch: 8.2 M
 // instead of 137 M), then per right-hand side: every thread applies its element to the staged values and parks the 10
-// results at their dof-major positions of a scratch; one thread per dof adds its consecutive entries (fixed order, no
+// results at their dof-major positions of a scratch; one thread per dof adds its entries (fixed order, no
 // shared-memory atomics), takes its p.q share and overwrites the staged value in place.  After the last pass one fp64
 // RED per (dof, right-hand side) adds the batch's share to Q, which is zeroed first.  Sums across batches are
 // RED-ordered, so Q is reproducible to rounding only.
@@ -39,6 +39,7 @@ constexpr int NLD = 10;   // local dofs of the P2 tet
 constexpr int KMAX = REMO_MAX_RHS;
 constexpr int EBE_MAX_RHS = 8;
 constexpr uint32_t SENT = 0xffffffffu;
+constexpr int EBE_JD = 264;  // jagged-diagonal offsets kept per batch (a dof has at most 256 entries in a batch)
 
 __global__ void k_tet_morton(const int32_t* __restrict__ sv, const double* __restrict__ xyz, const double* __restrict__ lohi,
                              int64_t nt, uint64_t* __restrict__ code, int32_t* __restrict__ idx) {
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(TPB) k_ebe_batch(SpaceView s, const int32_t* _
                                                    const uint8_t* __restrict__ constrained, int64_t* __restrict__ ucount,
                                                    int* __restrict__ umax, const int64_t* __restrict__ uoff,
                                                    int32_t* __restrict__ udof, uint16_t* __restrict__ lidx,
-                                                   uint16_t* __restrict__ lpos, uint16_t* __restrict__ incptr) {
+                                                   uint16_t* __restrict__ lpos, uint16_t* __restrict__ ucnt, uint16_t* __restrict__ jdp) {
   using Sort = cub::BlockRadixSort<uint32_t, TPB, NLD, uint16_t>;
   using Scan = cub::BlockScan<int, TPB>;
   __shared__ union Tmp {
@@ -109,25 +110,81 @@ __global__ void __launch_bounds__(TPB) k_ebe_batch(SpaceView s, const int32_t* _
     }
     return;
   }
+  // The scratch of the product kernel is laid out as JAGGED DIAGONALS: the dofs of the batch are ranked by their number
+  // of entries (descending) and entry i of the dof with rank u lives at jd[i] + u, jd[i] = number of entries with a
+  // smaller index i.  One thread per dof then walks i = 0 .. count-1: neighbouring lanes read neighbouring words (no
+  // bank conflicts) and the lanes of a warp have (almost) the same trip count -- a vertex has 20-40 entries in a
+  // batch, an edge ~3, and in dof order they would share warps.
+  __shared__ uint16_t spos[TPB * NLD + 1];  // first sorted position of every dof (by its rank in dof order)
+  __shared__ uint16_t snew[TPB * NLD];      // rank in dof order -> rank by entry count
+  __shared__ uint16_t sjd[EBE_JD];
+  const int nvalid = (int)((s.nt - (int64_t)b * TPB < TPB ? s.nt - (int64_t)b * TPB : TPB) * NLD);
+  {
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < NLD; k++)
+      if (head[k]) spos[base + cnt++] = (uint16_t)(tid * NLD + k);
+    if (tid == 0) spos[total] = (uint16_t)nvalid;  // padding tets sort behind every real entry
+  }
+  __syncthreads();
+  uint32_t ckey[NLD];
+  uint16_t cval[NLD];
+#pragma unroll
+  for (int k = 0; k < NLD; k++) {
+    const int rho = tid * NLD + k;
+    ckey[k] = rho < total ? 0xffffu - (uint32_t)(spos[rho + 1] - spos[rho]) : SENT;
+    cval[k] = (uint16_t)rho;
+  }
+  Sort(tmp.sort).Sort(ckey, cval);
+  uint32_t* scount = skey;  // entry counts by new rank (descending); the sorted dof keys are no longer needed
+#pragma unroll
+  for (int k = 0; k < NLD; k++) {
+    const int j = tid * NLD + k;
+    if (j < total) {
+      snew[cval[k]] = (uint16_t)j;
+      scount[j] = 0xffffu - ckey[k];
+    }
+  }
+  __syncthreads();
+  int ng[NLD], jd[NLD];
+#pragma unroll
+  for (int k = 0; k < NLD; k++) {  // dofs with more than i entries = first new rank whose count is <= i
+    const uint32_t i = (uint32_t)(tid * NLD + k);
+    int lo = 0, hi = total;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (scount[mid] > i) lo = mid + 1; else hi = mid;
+    }
+    ng[k] = lo;
+  }
+  Scan(tmp.scan).ExclusiveSum(ng, jd);
   const int64_t u0 = uoff[b];
   const int64_t bo = (int64_t)b * (TPB * NLD);
+#pragma unroll
+  for (int k = 0; k < NLD; k++) {
+    const int i = tid * NLD + k;
+    if (i < EBE_JD) {
+      sjd[i] = (uint16_t)jd[k];
+      jdp[(int64_t)b * EBE_JD + i] = (uint16_t)jd[k];
+    }
+  }
+  __syncthreads();
   int cnt = 0;
 #pragma unroll
   for (int k = 0; k < NLD; k++) {
     const int pos = tid * NLD + k;
+    if (head[k]) cnt++;
+    const int rho = base + cnt - 1;  // rank (dof order) of the dof this entry belongs to
+    const bool real = key[k] != SENT;
+    const int nr = real ? snew[rho] : 0;
     if (head[k]) {
-      const int rank = base + cnt;
-      cnt++;
-      udof[u0 + rank] = (int32_t)(key[k] | (constrained[key[k]] ? 0x80000000u : 0u));
-      incptr[u0 + b + rank] = (uint16_t)pos;
+      udof[u0 + nr] = (int32_t)(key[k] | (constrained[key[k]] ? 0x80000000u : 0u));
+      ucnt[u0 + nr] = (uint16_t)(spos[rho + 1] - spos[rho]);
     }
-    const int rank = base + cnt - 1;  // distinct dofs at positions <= pos, minus one
-    lidx[bo + val[k]] = (uint16_t)(key[k] != SENT ? rank : 0);
-    lpos[bo + val[k]] = (uint16_t)pos;  // padding tets sort behind every real entry
-  }
-  if (tid == 0) {
-    const int64_t left = s.nt - (int64_t)b * TPB;
-    incptr[u0 + b + total] = (uint16_t)((left < TPB ? left : TPB) * NLD);
+    lidx[bo + val[k]] = (uint16_t)nr;
+    // a dof appears at most once per tet: at most 256 entries, so i < EBE_JD.  Padding tets keep a slot behind the
+    // nvalid real entries
+    lpos[bo + val[k]] = (uint16_t)(real ? sjd[pos - spos[rho]] + nr : pos);
   }
 }
 
@@ -188,7 +245,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __global__ void __launch_bounds__(TPB, 3) k_spmm_ebe(int nb, const int64_t* __restrict__ uoff, const int32_t* __restrict__ udof,
                                                      const uint16_t* __restrict__ lidx, const uint16_t* __restrict__ lpos,
-                                                     const uint16_t* __restrict__ incptr, const double* __restrict__ gmb,
+                                                     const uint16_t* __restrict__ ucnt, const uint16_t* __restrict__ jdp,
+                                                     const double* __restrict__ gmb,
                                                      const double* __restrict__ P, int pstride, double* __restrict__ Q, int ks,
                                                      int nr, int xst, int umax, double* __restrict__ partial) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -198,7 +256,8 @@ __global__ void __launch_bounds__(TPB, 3) k_spmm_ebe(int nb, const int64_t* __re
   unsigned char* xs = smem_raw;
   double* scr = reinterpret_cast<double*>(xs + (size_t)umax * xst * 8);
   int32_t* sdof = reinterpret_cast<int32_t*>(scr + NLD * TPB);
-  uint16_t* sptr = reinterpret_cast<uint16_t*>(sdof + umax);
+  uint16_t* scnt = reinterpret_cast<uint16_t*>(sdof + umax);
+  uint16_t* sjd = scnt + umax;
   __shared__ double sdot[TPB / 32][EBE_MAX_RHS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fr = tid & 7;  // staging / flush: 8 lanes per dof row, lane = right-hand side
@@ -208,7 +267,8 @@ __global__ void __launch_bounds__(TPB, 3) k_spmm_ebe(int nb, const int64_t* __re
     const int64_t u0 = uoff[b];
     const int U = (int)(uoff[b + 1] - u0);
     for (int i = tid; i < U; i += TPB) sdof[i] = udof[u0 + i];
-    for (int i = tid; i <= U; i += TPB) sptr[i] = incptr[u0 + b + i];
+    for (int i = tid; i < U; i += TPB) scnt[i] = ucnt[u0 + i];
+    for (int i = tid; i < EBE_JD; i += TPB) sjd[i] = jdp[(int64_t)b * EBE_JD + i];
     __syncthreads();
     // stage the U rows of P: every copy of the batch is issued before anything waits (cp.async, 8 bytes per lane)
     if (fr < nr) {
@@ -244,18 +304,19 @@ __global__ void __launch_bounds__(TPB, 3) k_spmm_ebe(int nb, const int64_t* __re
         for (int k = 0; k < NLD; k++) *reinterpret_cast<double*>(sb + ((lso[k >> 1] >> ((k & 1) * 16)) & 0xffffu)) = y[k];
       }
       __syncthreads();
-      // per dof: its entries are consecutive in scr; fixed order, no atomics.  Dofs come sorted by number, i.e. the
-      // vertices (20-40 entries) first and together in the first warps, then the edges (~4 entries)
+      // one thread per dof (ranked by entry count): entry i of dof u sits at sjd[i] + u -- conflict-free, equal trip
+      // counts inside a warp, fixed order, no atomics
       double d = 0.0;
       for (int u = tid; u < U; u += TPB) {
-        const double* e = scr + sptr[u];
-        int n = (int)sptr[u + 1] - (int)sptr[u];
+        const double* e = scr + u;
+        const int n = scnt[u];
         double s0 = 0.0, s1 = 0.0;
-        for (; n >= 2; n -= 2, e += 2) {
-          s0 += e[0];
-          s1 += e[1];
+        int i = 0;
+        for (; i + 2 <= n; i += 2) {
+          s0 += e[sjd[i]];
+          s1 += e[sjd[i + 1]];
         }
-        if (n) s0 += e[0];
+        if (i < n) s0 += e[sjd[i]];
         s0 += s1;
         double* px = reinterpret_cast<double*>(xs + u * xstep + r * 8);
         if (sdof[u] >= 0) d = fma(s0, *px, d);  // p.q: constrained rows do not count (and are not written to Q)
@@ -285,7 +346,7 @@ __global__ void __launch_bounds__(TPB, 3) k_spmm_ebe(int nb, const int64_t* __re
 
 size_t ebe_smem(int umax, int nr) {
   const int xst = nr | 1;
-  return (size_t)umax * xst * 8 + (size_t)NLD * TPB * 8 + (size_t)umax * 4 + (size_t)(umax + 2) * 2;
+  return (size_t)umax * xst * 8 + (size_t)NLD * TPB * 8 + (size_t)umax * 4 + (size_t)(umax + EBE_JD) * 2;
 }
 
 }  // namespace
@@ -324,7 +385,7 @@ void ebe_build(Ctx* c) {
   int* umax_d = scratch<int>(c, 6, 1);
   CK(cudaMemsetAsync(umax_d, 0, sizeof(int), st));
   SpaceView sview = make_view(c);
-  LAUNCH(c, k_ebe_batch<false>, (unsigned)nb, TPB, 0, sview, tperm, c->constrained.p, ucount, umax_d, nullptr, nullptr, nullptr, nullptr, nullptr);
+  LAUNCH(c, k_ebe_batch<false>, (unsigned)nb, TPB, 0, sview, tperm, c->constrained.p, ucount, umax_d, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
   LAUNCH(c, k_ebe_offsets_in, grid_for(nb + 1, TPB), TPB, 0, ucount, nb, uin);
   c->ebe_uoff.ensure(nb + 1, st);
   CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, uin, c->ebe_uoff.p, nb + 1, st));
@@ -339,12 +400,13 @@ void ebe_build(Ctx* c) {
   umax = (umax + 1) & ~1;  // even: the 16-byte alignment of the shared-memory arrays behind xs
   // pass 2: tables
   c->ebe_udof.ensure(total, st);
-  c->ebe_incptr.ensure(total + nb + 1, st);
+  c->ebe_ucnt.ensure(total, st);
+  c->ebe_jd.ensure((size_t)nb * EBE_JD, st);
   c->ebe_lidx.ensure((size_t)nb * TPB * NLD, st);
   c->ebe_lpos.ensure((size_t)nb * TPB * NLD, st);
   c->ebe_gm.ensure((size_t)nb * TPB * NLD, st);
   LAUNCH(c, k_ebe_batch<true>, (unsigned)nb, TPB, 0, sview, tperm, c->constrained.p, nullptr, nullptr, c->ebe_uoff.p, c->ebe_udof.p,
-         c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_incptr.p);
+         c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_ucnt.p, c->ebe_jd.p);
   LAUNCH(c, k_ebe_gm, grid_for(nb * TPB, TPB), TPB, 0, c->gm.p, tperm, nt, nb, c->ebe_gm.p);
   c->ebe_nb = nb;
   c->ebe_umax = umax;
@@ -369,7 +431,7 @@ void launch_spmm_ebe(Ctx* c, const double* P, int pstride, double* Q, int ks, in
   const int xst = nr | 1;
   const int grid = ebe_grid(c, nr);
   const size_t sm = ebe_smem(c->ebe_umax, nr);
-  k_spmm_ebe<<<grid, TPB, sm, st>>>((int)c->ebe_nb, c->ebe_uoff.p, c->ebe_udof.p, c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_incptr.p, c->ebe_gm.p,
+  k_spmm_ebe<<<grid, TPB, sm, st>>>((int)c->ebe_nb, c->ebe_uoff.p, c->ebe_udof.p, c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_ucnt.p, c->ebe_jd.p, c->ebe_gm.p,
                                     P, pstride, Q, ks, nr, xst, c->ebe_umax, c->partial.p);
   c->launches += 2;
   CK(cudaGetLastError());
