@@ -119,6 +119,14 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+SPMM_KERNELS = {
+    0: "k_spmm_p / k_spmm_g (CSR PCG SpMM + fused p.q)",
+    1: "k_spmm_stream8 (SELL-8 PCG SpMM + fused p.q, cp.async-staged matrix stream)",
+    2: "k_spmm_ebe (element-wise PCG product Q = A P + fused p.q from 10 metric numbers per tet, no assembled matrix read; "
+       "includes the memset of Q; bytes counted as the CSR SpMM it replaces, SURVEY 8d)",
+}
+
+
 def spmm_bytes(nnz, ndof, k):
     """Algorithmic bytes of one SpMM launch: fp64 values + int32 columns, int64 row pointers, P read once,
     Q written once: 12 nnz + N (8 + 16 k)."""
@@ -239,6 +247,7 @@ def run_b200(args):
     ms_prof = timed(dev, args.steps, contexts=1)
     spmm_ms, spmm_n = ctx.profile_get()
     ctx.profile(False)
+    kind = ctx.spmm_kind()  # 0 CSR, 1 SELL copy, 2 element-wise (remo_spmm_kind)
     stage = ctx.stage_times()  # of the last step of the single-context leg (under two contexts the stages interleave)
     if os.environ.get("REMO_BENCH_DEBUG"):
         log("debug: dev %.1f ms, e2e %.1f ms, profiled (no graph) %.1f ms" % (ms_dev, ms_e2e, ms_prof))
@@ -258,8 +267,8 @@ def run_b200(args):
         per_launch = spmm_ms / max(spmm_n, 1) / 1e3
         traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per SpMM launch from the committed ncu --set full capture
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_spmm_traffic_%s.json" % args.size)))
-            if tj.get("order") == args.order and tj.get("nrhs") == nrhs:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_spmm%s_traffic_%s.json" % ("_ebe" if kind == 2 else "", args.size))))
+            if tj.get("order") == args.order and tj.get("nrhs") == nrhs and kind != 0:
                 traffic = tj["traffic_bytes_per_launch"]
         except Exception:
             pass
@@ -284,7 +293,7 @@ def run_b200(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_spmm_stream8 (SELL-8 PCG SpMM + fused p.q, cp.async-staged matrix stream)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": SPMM_KERNELS[kind], "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "bytes_per_launch": spmm_bytes(nnz, ndof, nrhs), "avg_launch_ms": per_launch * 1e3, "launches_timed": int(spmm_n),
                          "frac_of_8TBs_spec": achieved / 8000.0, "spmm_share_of_step": spmm_ms / ms_prof,

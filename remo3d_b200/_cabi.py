@@ -42,6 +42,7 @@ SIGNATURES = {
     "remo_profile": (C.c_int, [_p, C.c_int]),
     "remo_profile_get": (C.c_int, [_p, C.POINTER(C.c_double), _i64p]),
     "remo_launch_count": (C.c_int64, [_p]),
+    "remo_spmm_kind": (C.c_int, [_p]),
     "remo_stage_times": (C.c_int, [_p, _p]),
 }
 
@@ -216,6 +217,10 @@ class Context:
         pq = np.empty(p.shape[1])
         self._ck(self.lib.remo_spmm_apply(self.h, p.shape[1], p.ctypes.data, q.ctypes.data, pq.ctypes.data))
         return q, pq
+
+    def spmm_kind(self):
+        """0 = CSR, 1 = SELL copy, 2 = element-wise product (for the right-hand sides currently set)."""
+        return int(self.lib.remo_spmm_kind(self.h))
 
     def set_option(self, name, value):
         self._ck(self.lib.remo_set_option(self.h, name.encode(), float(value)))

@@ -296,6 +296,7 @@ int remo_kernel_time(void* vctx, int which, int nrhs, int reps, float* ms) {
         c->have_solution = false;
       }
       if (c->pkind < 0) precond_setup(c, REMO_PRECOND_LOCAL);
+      spmm_prepare(c);
       // deterministic non-trivial vectors: P = dinv-scaled ones pattern is not needed for timing; reuse F
       CK(cudaMemcpy2DAsync(c->P.p, (size_t)c->pstride * sizeof(double), c->F.p, (size_t)c->nrhs * sizeof(double), (size_t)c->nrhs * sizeof(double), (size_t)c->ndof, cudaMemcpyDeviceToDevice, st));
       CK(cudaMemsetAsync(c->scal.p, 0, c->scal.n * sizeof(double), st));
@@ -335,6 +336,7 @@ int remo_spmm_apply(void* vctx, int nrhs, const double* p, double* q, double* pq
     const size_t w = (size_t)nrhs * sizeof(double);
     CK(cudaMemsetAsync(c->P.p, 0, (size_t)c->ndof * c->pstride * sizeof(double), st));
     CK(cudaMemcpy2DAsync(c->P.p, (size_t)c->pstride * sizeof(double), p, w, w, (size_t)c->ndof, cudaMemcpyDefault, st));
+    spmm_prepare(c);
     launch_spmm(c, c->P.p, c->Q.p, ks);
     CK(cudaMemcpy2DAsync(q, w, c->Q.p, (size_t)ks * sizeof(double), w, (size_t)c->ndof, cudaMemcpyDefault, st));
     const int nblk = spmm_blocks(c, ks);
@@ -348,6 +350,12 @@ int remo_spmm_apply(void* vctx, int nrhs, const double* p, double* q, double* pq
     }
     return REMO_OK;
   });
+}
+
+int remo_spmm_kind(void* vctx) {
+  Ctx* c = static_cast<Ctx*>(vctx);
+  if (!c) return REMO_ERR_ARG;
+  return spmm_kind(c);
 }
 
 int remo_set_option(void* vctx, const char* name, double value) {

@@ -224,6 +224,8 @@ void launch_spmm(Ctx* c, const double* P, double* Q, int nrhs);
 void launch_vector_updates(Ctx* c, int nrhs);
 void alloc_solver_state(Ctx* c, int nrhs);
 int spmm_variant();
+void spmm_prepare(Ctx* c);
+int spmm_kind(Ctx* c);
 int solver_stride(int nrhs);       // row stride of the PCG vector blocks for nrhs right-hand sides
 int spmm_blocks(Ctx* c, int ks);   // CTAs (= partial-dot slots) of the SpMM launch for stride ks
 // sell.cu

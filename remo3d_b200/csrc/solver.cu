@@ -631,6 +631,18 @@ void launch_spmm(Ctx* c, const double* P, double* Q, int nrhs) {
   CK(cudaGetLastError());
 }
 
+// after alloc_solver_state / the right-hand sides are known: make sure the matrix copy the chosen SpMM kernel reads exists
+void spmm_prepare(Ctx* c) {
+  if (!c->have_matrix || use_ebe(c, c->P.p)) return;
+  if (spmm_variant() >= 5 && c->pstride >= 2 && !c->have_sell) sell_build(c);
+}
+
+// 0 = CSR kernels, 1 = SELL copy, 2 = element-wise (for remo_spmm_kind)
+int spmm_kind(Ctx* c) {
+  if (use_ebe(c, c->P.p)) return 2;
+  return use_sell(c, c->nrhs, c->P.p) ? 1 : 0;
+}
+
 void launch_vector_updates(Ctx* c, int nrhs) {
   const int grid = vec_grid(c, nrhs);
   DISPATCH_W(nrhs, (k_update_xr<W><<<grid, TB, 0, c->stream>>>(c->X.p, c->R.p, c->P.p, c->Q.p, c->dinv.p, c->Z.p, c->scal.p, nrhs, c->pstride, c->ndof, (int64_t)0, c->partial.p)));
@@ -646,8 +658,10 @@ void precond_setup(Ctx* c, int kind) {
   c->dinv.ensure(c->ndof, c->stream);
   LAUNCH(c, k_dinv, grid_for(c->ndof, TB), TB, 0, c->rowptr.p, c->col.p, c->val.p, c->constrained.p, c->dinv.p, c->ndof);
   if (kind == REMO_PRECOND_MULTIGRID) amg_setup(c);
-  if (spmm_variant() >= 5 && !c->have_sell) sell_build(c);
-  if (ebe_eligible(c) && !c->have_ebe) ebe_build(c);
+  // order-2 tets: the element-wise product needs no second copy of the matrix; the SELL copy is made on demand
+  // (spmm_prepare) if a block wider than ebe.cu takes shows up
+  if (ebe_eligible(c)) { if (!c->have_ebe) ebe_build(c); }
+  else if (spmm_variant() >= 5 && !c->have_sell) sell_build(c);
   c->pkind = kind;
 }
 
@@ -689,6 +703,7 @@ int solve(Ctx* c, double rtol, int maxit, int* iters, double* relres) {
   if (!c->have_rhs) FAIL(REMO_ERR_STATE, "remo_solve: no right-hand side (call remo_rhs_point_sources first)");
   if (!(rtol > 0.0) || maxit < 1) FAIL(REMO_ERR_ARG, "remo_solve: rtol must be > 0 and maxit >= 1");
   StageTimer timer(c, ST_SOLVE);
+  spmm_prepare(c);
   cudaStream_t st = c->stream;
   const int k = c->nrhs, kp = kp_for(k);
   const int64_t n = c->ndof;

@@ -85,6 +85,35 @@ def _quadratic_interpolant(space, pts, u):
     return x
 
 
+def test_p2_tet_closed_form_matches_tensors():
+    """The closed form remo3d_b200/csrc/ebe.cu (p2_apply) uses for y = K_e x on an order-2 tet -- written from
+    grad u = sum_j c_j(l) grad l_j with c_j linear in the barycentrics -- against K_e = sum_m S_m T[m] with the exact
+    reference tensors, for random metric numbers and vectors."""
+    T = fo.reference_tensors(3, 2)[0]
+    pairs = fo.metric_pairs(3)
+    le = fo.local_edges(3)
+    rng = np.random.default_rng(11)
+    for _ in range(20):
+        g = rng.standard_normal((4, 3))
+        g[0] = -(g[1] + g[2] + g[3])
+        S = g @ g.T
+        K = np.einsum("m,mab->ab", np.array([S[i, j] for i, j in pairs]), T)
+        x = rng.standard_normal(10)
+        xe = np.zeros((4, 4))
+        for e, (a, b) in enumerate(le):
+            xe[a, b] = xe[b, a] = x[4 + e]
+        sj = xe.sum(axis=1)
+        d0 = x[:4] + 0.25 * sj          # mean of c_j
+        bs = 0.25 * x[:4] + 0.05 * sj   # mean of l_a c_j without the x_{ja} term
+        y = np.empty(10)
+        y[:4] = S @ d0
+        B = S @ bs
+        V = S @ xe                      # V[b][a] = sum_j S_bj xe[j][a]
+        for e, (a, b) in enumerate(le):
+            y[4 + e] = B[a] + B[b] + 0.05 * (V[b, a] + V[a, b])
+        assert np.max(np.abs(y - K @ x)) <= 1e-14 * np.max(np.abs(K)) * np.max(np.abs(x)) * 10
+
+
 @pytest.mark.parametrize("order", [1, 2, 3])
 def test_energy_of_polynomials_is_exact(order):
     pts, elems, bf, bc = meshgen.box_mesh(3)
