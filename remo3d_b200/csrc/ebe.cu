@@ -63,7 +63,7 @@ __global__ void k_tet_morton(const int32_t* __restrict__ sv, const double* __res
 // One CTA per batch.  FILL = false: count the distinct dofs; true: write the batch tables at the offsets uoff[].
 template <bool FILL>
 __global__ void __launch_bounds__(TPB) k_ebe_batch(SpaceView s, const int32_t* __restrict__ tperm,
-                                                   const uint8_t* __restrict__ constrained, int64_t* __restrict__ ucount,
+                                                   int split, const uint8_t* __restrict__ constrained, int64_t* __restrict__ ucount,
                                                    int* __restrict__ umax, const int64_t* __restrict__ uoff,
                                                    int32_t* __restrict__ udof, uint16_t* __restrict__ lidx,
                                                    uint16_t* __restrict__ lpos, uint16_t* __restrict__ ucnt, uint16_t* __restrict__ jdp) {
@@ -100,6 +100,17 @@ __global__ void __launch_bounds__(TPB) k_ebe_batch(SpaceView s, const int32_t* _
   for (int k = 0; k < NLD; k++) {
     const int pos = tid * NLD + k;
     head[k] = key[k] != SENT && (pos == 0 || skey[pos - 1] != key[k]);
+    if (split > 0 && key[k] != SENT && !head[k]) {
+      // a dof with many entries in the batch (a vertex: up to 40) is cut into pieces of `split` entries; every piece is
+      // a dof of its own for the product kernel (staged, summed and added to Q separately), so no thread of the per-dof
+      // sums runs much longer than the others
+      int lo = pos > TPB ? pos - TPB : 0, hi = pos;  // first entry of this dof: a dof has at most 256 entries
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (skey[mid] < key[k]) lo = mid + 1; else hi = mid;
+      }
+      head[k] = ((pos - lo) % split) == 0;
+    }
     heads += head[k] ? 1 : 0;
   }
   int base = 0, total = 0;
@@ -380,13 +391,14 @@ void ebe_build(Ctx* c) {
   c->tmp.ensure(bytes, st);
   CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, code, codes, idx, tperm, nt, 0, 63, st));
   c->launches += 4;
+  static const int split = [] { const char* e = getenv("REMO_EBE_SPLIT"); return e ? atoi(e) : 8; }();
   // pass 1: distinct dofs per batch -> offsets
   int64_t* ucount = scratch<int64_t>(c, 4, nb + 1);
   int64_t* uin = scratch<int64_t>(c, 5, nb + 1);
   int* umax_d = scratch<int>(c, 6, 1);
   CK(cudaMemsetAsync(umax_d, 0, sizeof(int), st));
   SpaceView sview = make_view(c);
-  LAUNCH(c, k_ebe_batch<false>, (unsigned)nb, TPB, 0, sview, tperm, c->constrained.p, ucount, umax_d, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  LAUNCH(c, k_ebe_batch<false>, (unsigned)nb, TPB, 0, sview, tperm, split, c->constrained.p, ucount, umax_d, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
   LAUNCH(c, k_ebe_offsets_in, grid_for(nb + 1, TPB), TPB, 0, ucount, nb, uin);
   c->ebe_uoff.ensure(nb + 1, st);
   CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, uin, c->ebe_uoff.p, nb + 1, st));
@@ -406,7 +418,7 @@ void ebe_build(Ctx* c) {
   c->ebe_lidx.ensure((size_t)nb * TPB * NLD, st);
   c->ebe_lpos.ensure((size_t)nb * TPB * NLD, st);
   c->ebe_gm.ensure((size_t)nb * TPB * NLD, st);
-  LAUNCH(c, k_ebe_batch<true>, (unsigned)nb, TPB, 0, sview, tperm, c->constrained.p, nullptr, nullptr, c->ebe_uoff.p, c->ebe_udof.p,
+  LAUNCH(c, k_ebe_batch<true>, (unsigned)nb, TPB, 0, sview, tperm, split, c->constrained.p, nullptr, nullptr, c->ebe_uoff.p, c->ebe_udof.p,
          c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_ucnt.p, c->ebe_jd.p);
   LAUNCH(c, k_ebe_gm, grid_for(nb * TPB, TPB), TPB, 0, c->gm.p, tperm, nt, nb, c->ebe_gm.p);
   c->ebe_nb = nb;

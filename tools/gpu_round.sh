@@ -1,16 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-L=gpurun_out/final1.log
+L=gpurun_out/ebe7.log
 : > $L
-timeout 1000 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 >> $L
-python bench.py > gpurun_out/bench_default_ebe.json 2> gpurun_out/bench_default_ebe.err; echo "bench rc=$?" >> $L
-REMO_SPMM_EBE=0 python bench.py --no-cpu-baseline > gpurun_out/bench_default_sell.json 2> gpurun_out/bench_default_sell.err; echo "bench sell rc=$?" >> $L
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_5M_ebe.csv \
-  python bench.py --steps 1 --warmup 1 --no-cpu-baseline --contexts 1 > gpurun_out/ncu_launch_ebe.log 2>&1; echo "launch list rc=$?" >> $L
-REMO_PROBE_SIZE=5M timeout 500 ncu --set full --clock-control none --import-source on -k regex:k_spmm_ebe -s 30 -c 2 -o gpurun_out/ebe_k5_5M -f \
-  python tools/spmm_probe.py --ks 5 > gpurun_out/ncu_ebe_5M.log 2>&1; echo "ncu full rc=$?" >> $L
-python -c "
-import json
-for f in ('ebe','sell'):
-    d=json.load(open('gpurun_out/bench_default_%s.json'%f)); print(f, d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['iterations'], d['roofline']['frac'], d['roofline']['avg_launch_ms'], d['roofline']['kernel'][:20])" >> $L 2>&1
+timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "spmm or block_sizes" 2>&1 | tail -4 >> $L
+for sp in 8 0 4 16; do
+echo "SPLIT=$sp" >> $L
+REMO_EBE_SPLIT=$sp REMO_PROBE_SIZE=5M timeout 400 python tools/spmm_probe.py --ks 5,6,2,1 2>&1 | grep "^k=\|rror" >> $L
+done
 cat $L
