@@ -121,6 +121,7 @@ struct Ctx {
   DBuf<double> ebe_gm;        // nb x 10 x 256: metric numbers in batch order
   int64_t ebe_nb = 0;
   int ebe_umax = 0;
+  int ebe_fast8 = 0;  // every dof piece has <= 8 entries and every batch <= 1024 of them: register tables in the kernel
   int ebe_occ[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // resident CTAs per SM by right-hand-side count
   bool have_ebe = false;
   int ebe_on = -1;  // remo_set_option("spmm_ebe"): 0 / 1, -1 = the REMO_SPMM_EBE environment default (on)

@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(TPB, 3) k_spmm_ebe(int nb, const int64_t* __re
                                                      const uint16_t* __restrict__ ucnt, const uint16_t* __restrict__ jdp,
                                                      const double* __restrict__ gmb,
                                                      const double* __restrict__ P, int pstride, double* __restrict__ Q, int ks,
-                                                     int nr, int xst, int umax, double* __restrict__ partial) {
+                                                     int nr, int xst, int umax, int fast8, double* __restrict__ partial) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // xs: umax x xst staged rows of P (xst odd: random rows spread over the banks); column r is overwritten in place by
   // the batch's share of Q once pass r no longer needs it.  scr: the element results of the current pass in SORTED
@@ -302,6 +302,17 @@ __global__ void __launch_bounds__(TPB, 3) k_spmm_ebe(int nb, const int64_t* __re
     }
 #pragma unroll
     for (int k = 0; k < NLD; k++) g[k] = __ldcs(gmb + ((int64_t)b * NLD + k) * TPB + tid);
+    // fast8: entry counts (+ constrained flag in bit 7) of this thread's up to four dofs, and the first 8 diagonal offsets
+    uint32_t info = 0, jdr[4] = {0, 0, 0, 0};
+    if (fast8) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int u = tid + j * TPB;
+        if (u < U) info |= ((uint32_t)scnt[u] | (sdof[u] < 0 ? 0x80u : 0u)) << (8 * j);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) jdr[i] = (uint32_t)sjd[2 * i] | ((uint32_t)sjd[2 * i + 1] << 16);
+    }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     for (int r = 0; r < nr; r++) {
@@ -316,23 +327,46 @@ __global__ void __launch_bounds__(TPB, 3) k_spmm_ebe(int nb, const int64_t* __re
         for (int k = 0; k < NLD; k++) *reinterpret_cast<double*>(sb + ((lso[k >> 1] >> ((k & 1) * 16)) & 0xffffu)) = y[k];
       }
       __syncthreads();
-      // one thread per dof (ranked by entry count): entry i of dof u sits at sjd[i] + u -- conflict-free, equal trip
+      // one thread per dof (ranked by entry count): entry i of dof u sits at jd[i] + u -- conflict-free, equal trip
       // counts inside a warp, fixed order, no atomics
       double d = 0.0;
-      for (int u = tid; u < U; u += TPB) {
-        const double* e = scr + u;
-        const int n = scnt[u];
-        double s0 = 0.0, s1 = 0.0;
-        int i = 0;
-        for (; i + 2 <= n; i += 2) {
-          s0 += e[sjd[i]];
-          s1 += e[sjd[i + 1]];
+      if (fast8) {
+        // every dof has at most 8 entries and the batch at most 1024 dofs: the diagonal offsets and this thread's entry
+        // counts stay in registers for all passes (no table loads in the loop)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int n = (int)((info >> (8 * j)) & 15u);
+          if (n) {
+            const int u = tid + j * TPB;
+            const double* e = scr + u;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              if (i < n) s0 += e[(jdr[i >> 1] & 0xffffu)];
+              if (i + 1 < n) s1 += e[(jdr[i >> 1] >> 16)];
+            }
+            s0 += s1;
+            double* px = reinterpret_cast<double*>(xs + u * xstep + r * 8);
+            if (!((info >> (8 * j + 7)) & 1u)) d = fma(s0, *px, d);  // p.q: constrained rows do not count
+            *px = s0;
+          }
         }
-        if (i < n) s0 += e[sjd[i]];
-        s0 += s1;
-        double* px = reinterpret_cast<double*>(xs + u * xstep + r * 8);
-        if (sdof[u] >= 0) d = fma(s0, *px, d);  // p.q: constrained rows do not count (and are not written to Q)
-        *px = s0;
+      } else {
+        for (int u = tid; u < U; u += TPB) {
+          const double* e = scr + u;
+          const int n = scnt[u];
+          double s0 = 0.0, s1 = 0.0;
+          int i = 0;
+          for (; i + 2 <= n; i += 2) {
+            s0 += e[sjd[i]];
+            s1 += e[sjd[i + 1]];
+          }
+          if (i < n) s0 += e[sjd[i]];
+          s0 += s1;
+          double* px = reinterpret_cast<double*>(xs + u * xstep + r * 8);
+          if (sdof[u] >= 0) d = fma(s0, *px, d);  // p.q: constrained rows do not count (and are not written to Q)
+          *px = s0;
+        }
       }
 #pragma unroll
       for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
@@ -422,6 +456,7 @@ void ebe_build(Ctx* c) {
          c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_ucnt.p, c->ebe_jd.p);
   LAUNCH(c, k_ebe_gm, grid_for(nb * TPB, TPB), TPB, 0, c->gm.p, tperm, nt, nb, c->ebe_gm.p);
   c->ebe_nb = nb;
+  c->ebe_fast8 = (split > 0 && split <= 8 && umax <= 4 * TPB) ? 1 : 0;
   c->ebe_umax = umax;
   // resident CTAs per SM for every right-hand-side count (the shared-memory row stride of xs depends on it)
   int dev_max = 0;
@@ -445,7 +480,7 @@ void launch_spmm_ebe(Ctx* c, const double* P, int pstride, double* Q, int ks, in
   const int grid = ebe_grid(c, nr);
   const size_t sm = ebe_smem(c->ebe_umax, nr);
   k_spmm_ebe<<<grid, TPB, sm, st>>>((int)c->ebe_nb, c->ebe_uoff.p, c->ebe_udof.p, c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_ucnt.p, c->ebe_jd.p, c->ebe_gm.p,
-                                    P, pstride, Q, ks, nr, xst, c->ebe_umax, c->partial.p);
+                                    P, pstride, Q, ks, nr, xst, c->ebe_umax, c->ebe_fast8, c->partial.p);
   c->launches += 2;
   CK(cudaGetLastError());
 }
