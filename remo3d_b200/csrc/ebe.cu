@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(TPB, 3) k_spmm_ebe(int nb, const int64_t* __re
                                                      const uint16_t* __restrict__ ucnt, const uint16_t* __restrict__ jdp,
                                                      const double* __restrict__ gmb,
                                                      const double* __restrict__ P, int pstride, double* __restrict__ Q, int ks,
-                                                     int nr, int xst, int umax, int fast8, double* __restrict__ partial) {
+                                                     int nr, int xst, int umax, int fast8, int pf, double* __restrict__ partial) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // xs: umax x xst staged rows of P (xst odd: random rows spread over the banks); column r is overwritten in place by
   // the batch's share of Q once pass r no longer needs it.  scr: the element results of the current pass in SORTED
@@ -278,6 +278,21 @@ __global__ void __launch_bounds__(TPB, 3) k_spmm_ebe(int nb, const int64_t* __re
   for (int b = blockIdx.x; b < nb; b += gridDim.x) {
     const int64_t u0 = uoff[b];
     const int U = (int)(uoff[b + 1] - u0);
+    if (pf && b + (int)gridDim.x < nb) {
+      // the tables of this CTA's next batch are first-touch DRAM reads: pull their lines into L2 now
+      const int64_t nb1 = b + gridDim.x;
+      const void* a = nullptr;
+      if (tid < 40) a = lidx + nb1 * (TPB * NLD) + tid * 64;
+      else if (tid < 80) a = lpos + nb1 * (TPB * NLD) + (tid - 40) * 64;
+      else if (tid < 240) a = gmb + nb1 * (TPB * NLD) + (tid - 80) * 16;
+      else if (tid < 245) a = jdp + nb1 * EBE_JD + (tid - 240) * 64;
+      if (a) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+      if (tid < 36) {
+        const int64_t un = uoff[nb1];
+        const void* a2 = tid < 24 ? (const void*)(udof + un + tid * 32) : (const void*)(ucnt + un + (tid - 24) * 64);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a2));
+      }
+    }
     for (int i = tid; i < U; i += TPB) sdof[i] = udof[u0 + i];
     for (int i = tid; i < U; i += TPB) scnt[i] = ucnt[u0 + i];
     for (int i = tid; i < EBE_JD; i += TPB) sjd[i] = jdp[(int64_t)b * EBE_JD + i];
@@ -478,9 +493,10 @@ void launch_spmm_ebe(Ctx* c, const double* P, int pstride, double* Q, int ks, in
   CK(cudaMemsetAsync(Q, 0, (size_t)c->ndof * ks * sizeof(double), st));
   const int xst = nr | 1;
   const int grid = ebe_grid(c, nr);
+  static const int pf = [] { const char* e = getenv("REMO_EBE_PREFETCH"); return e ? atoi(e) : 1; }();
   const size_t sm = ebe_smem(c->ebe_umax, nr);
   k_spmm_ebe<<<grid, TPB, sm, st>>>((int)c->ebe_nb, c->ebe_uoff.p, c->ebe_udof.p, c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_ucnt.p, c->ebe_jd.p, c->ebe_gm.p,
-                                    P, pstride, Q, ks, nr, xst, c->ebe_umax, c->ebe_fast8, c->partial.p);
+                                    P, pstride, Q, ks, nr, xst, c->ebe_umax, c->ebe_fast8, pf, c->partial.p);
   c->launches += 2;
   CK(cudaGetLastError());
 }
