@@ -299,6 +299,18 @@ def run_b200(args):
                          "frac_of_8TBs_spec": achieved / 8000.0, "spmm_share_of_step": spmm_ms / ms_prof,
                          "timed_with": "CUDA events around every SpMM launch in %d extra steps run right after the timed regions (plain launches instead of the CUDA graph)" % args.steps},
         }
+        try:
+            # numeric assembly (remo_assemble: geometry + atomic-free row-gather kernels + the sigma copy) against the same
+            # peak; algorithmic bytes per element as in SURVEY 8d: vertex ids + coordinates + material + the ldof^2 scatter
+            # map (4 B) and values (8 B)
+            ldof = {1: 4, 2: 10, 3: 20}[args.order]
+            abytes = float(m["elems"].shape[0]) * (16 + 96 + 4 + 12 * ldof * ldof)
+            ams = float(stage["assemble"])
+            line["assembly"] = {"ms": ams, "algorithmic_bytes": abytes, "achieved": abytes / ams / 1e6, "unit": "GB/s",
+                                "frac": abytes / ams / 1e6 / peak, "nnz_per_s": nnz / ams * 1e3,
+                                "note": "stage time of one context running alone (CUDA events on its stream)"}
+        except Exception as e:  # reporting only
+            line["assembly"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, log)
         emit(line)
