@@ -59,14 +59,16 @@ def make_mesh(size, task, log=lambda *a: None):
     from remo3d_b200 import meshgen
 
     he, ha, g, hm = SIZES[size]
-    key = hashlib.sha1(repr((size, he, ha, g, hm, task[1][0].tolist(), 3)).encode()).hexdigest()[:12]
+    # optional sliver pass of the mesher (meshgen.half_ball_mesh(improve=N)); 0 = the round-1 meshes
+    improve = int(os.environ.get("REMO_BENCH_MESH_IMPROVE", "0"))
+    key = hashlib.sha1(repr((size, he, ha, g, hm, task[1][0].tolist(), 3) + ((improve,) if improve else ())).encode()).hexdigest()[:12]
     path = os.path.join(os.environ.get("REMO_MESH_CACHE", tempfile.gettempdir()), "remo3d_bench_mesh_%s.npz" % key)
     if os.path.exists(path):
         z = np.load(path)
         return {k: z[k] for k in z.files}
     t0 = time.time()
     material = meshgen.layered_material([-1.0, 1.5], dip_rad=np.deg2rad(30.0), borehole_radius=0.1, inclusion=((3.0, 2.0, 1.0), 1.5))
-    m = meshgen.half_ball_mesh(50.0, task[1][0], material=material, h_electrode=he, h_axis=ha, grading=g, h_max=hm, seed=0)
+    m = meshgen.half_ball_mesh(50.0, task[1][0], material=material, h_electrode=he, h_axis=ha, grading=g, h_max=hm, seed=0, improve=improve)
     from remo3d_b200.mesh import Mesh
 
     mesh = Mesh(m["points"], m["elems"], m["mat"], m["bfacets"], m["bc"], m["bc_names"])
@@ -288,6 +290,7 @@ def run_b200(args):
                 "l2": "inputs larger than L2 (matrix %.0f MB + vectors %.0f MB vs 126 MB L2); no explicit flush" % (12e-6 * nnz, 48e-6 * ndof * nrhs),
                 "sharding": "independent mesh tasks per rank, no data-path collective",
                 "contexts_per_gpu": nctx, "stage_ms_one_context_alone": stage,
+                "mesh_sliver_pass_rounds": int(os.environ.get("REMO_BENCH_MESH_IMPROVE", "0")),
             },
             "e2e": {"value": e2e, "unit": "log points/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(npts * 8),
                     "ms_per_step": ms_e2e / args.steps},

@@ -269,16 +269,39 @@ def _quality(points, elems):
     return vol / (e2 ** 1.5) * (6.0 * np.sqrt(2.0))
 
 
+def _delaunay_peeled(pts, on_plane, radius, seed):
+    """Delaunay tets of the cloud with the flat tets of the symmetry plane and the boundary slivers removed."""
+    from scipy.spatial import Delaunay
+
+    # Qhull is ~10x slower with thousands of exactly coplanar hull points (the symmetry plane):
+    # triangulate a copy whose plane points are lifted by <= 2e-11 R, keep the exact coordinates;
+    # the flat tets this creates on the plane are boundary slivers and are peeled below
+    lifted = pts.copy()
+    lifted[on_plane, 1] += np.random.default_rng(seed).uniform(0.0, 2e-11 * radius, size=int(on_plane.sum()))
+    tri = Delaunay(lifted)
+    elems = tri.simplices.astype(np.int32)
+    elems = elems[~on_plane[elems].all(axis=1)]  # exactly flat tets lying in the symmetry plane
+    # peel boundary slivers (flat tets between nearly coplanar hull points)
+    for _ in range(6):
+        qual = _quality(pts, elems)
+        _, owner = boundary_facets(elems, return_owner=True)
+        drop = np.zeros(elems.shape[0], bool)
+        drop[owner] = True  # tets that own a boundary face ...
+        drop &= qual < 2e-2  # ... and are slivers
+        if not drop.any():
+            break
+        elems = elems[~drop]
+    return elems
+
+
 def half_ball_mesh(radius, electrodes_z, material=None, **kw):
     """Graded half-ball (or full ball with half=False) tet mesh.
 
     Returns dict(points, elems, mat, bfacets, bc, bc_names, n_axis); vertices are renumbered along a
     Morton curve for memory locality with the axis vertices kept as mesh vertices.  `material(centroids)`
     -> 0-based material index per tet (default: all 0)."""
-    from scipy.spatial import Delaunay
-
     half = kw.get("half", True)
-    pts, n_axis, _ = half_ball_points(radius, electrodes_z, **kw)
+    pts, n_axis, _ = half_ball_points(radius, electrodes_z, **{k: v for k, v in kw.items() if k not in ("improve", "improve_quality")})
     # Morton order with 21 bits per axis (locality of vertex numbers -> locality of CSR columns, at every
     # refinement level: the finest cells here are ~1e-4 of the domain)
     q = np.clip(((pts + radius) / (2 * radius) * (2 ** 21 - 1)).astype(np.uint64), 0, 2 ** 21 - 1)
@@ -293,25 +316,41 @@ def half_ball_mesh(radius, electrodes_z, material=None, **kw):
 
     code = spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1)) | (spread(q[:, 2]) << np.uint64(2))
     pts = pts[np.argsort(code, kind="stable")]
-    # Qhull is ~10x slower with thousands of exactly coplanar hull points (the symmetry plane):
-    # triangulate a copy whose plane points are lifted by <= 2e-11 R, keep the exact coordinates;
-    # the flat tets this creates on the plane are boundary slivers and are peeled below
-    lifted = pts.copy()
-    on_plane = lifted[:, 1] == 0.0
-    lifted[on_plane, 1] += np.random.default_rng(kw.get("seed", 0) + 1).uniform(0.0, 2e-11 * radius, size=int(on_plane.sum()))
-    tri = Delaunay(lifted)
-    elems = tri.simplices.astype(np.int32)
-    elems = elems[~on_plane[elems].all(axis=1)]  # exactly flat tets lying in the symmetry plane
-    # peel boundary slivers (flat tets between nearly coplanar hull points)
-    for _ in range(6):
-        qual = _quality(pts, elems)
-        _, owner = boundary_facets(elems, return_owner=True)
-        drop = np.zeros(elems.shape[0], bool)
-        drop[owner] = True  # tets that own a boundary face ...
-        drop &= qual < 2e-2  # ... and are slivers
-        if not drop.any():
-            break
-        elems = elems[~drop]
+    on_plane = pts[:, 1] == 0.0
+    elems = _delaunay_peeled(pts, on_plane, radius, kw.get("seed", 0) + 1)
+    # optional quality pass (off by default): Delaunay meshes of well-spaced points still hold SLIVERS (four nearly
+    # coplanar, nearly cocircular points), and the slivers -- not the point spacing -- set the condition number the PCG
+    # sees.  Vertices of the worst tets that are free to move (not on the axis, the symmetry plane or the sphere) are
+    # perturbed by a fraction of the local edge length and the cloud is re-triangulated; the best mesh is kept.
+    improve = int(kw.get("improve", 0))
+    if improve > 0:
+        rng = np.random.default_rng(kw.get("seed", 0) + 7)
+        qmin = float(kw.get("improve_quality", 0.12))
+        fixed = on_plane | ((pts[:, 0] == 0.0) & (pts[:, 1] == 0.0)) | (np.linalg.norm(pts, axis=1) >= radius * (1 - 1e-6))
+        best = (int((_quality(pts, elems) < qmin).sum()), pts, elems)
+        for it in range(improve):
+            qual = _quality(pts, elems)
+            bad = np.where(qual < qmin)[0]
+            if bad.size == 0:
+                break
+            x = pts[elems[bad]]
+            h = np.sqrt(sum(((x[:, i] - x[:, j]) ** 2).sum(axis=1) for i in range(4) for j in range(i + 1, 4)) / 6.0)
+            hv = np.full(pts.shape[0], np.inf)
+            np.minimum.at(hv, elems[bad].ravel(), np.repeat(h, 4))
+            move = np.where(np.isfinite(hv) & ~fixed)[0]
+            if move.size == 0:
+                break
+            step = rng.standard_normal((move.size, 3))
+            step *= (0.18 * hv[move] / np.linalg.norm(step, axis=1))[:, None]
+            pts = pts.copy()
+            pts[move] += step
+            if half:
+                pts[move, 1] = np.abs(pts[move, 1])  # stay on this side of the symmetry plane
+            elems = _delaunay_peeled(pts, on_plane, radius, kw.get("seed", 0) + 1 + it)
+            nbad = int((_quality(pts, elems) < qmin).sum())
+            if nbad < best[0]:
+                best = (nbad, pts, elems)
+        _, pts, elems = best
     # positive orientation
     x = pts[elems]
     neg = np.linalg.det(x[:, 1:] - x[:, :1]) < 0

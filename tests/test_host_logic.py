@@ -179,3 +179,34 @@ def test_save_results_is_byte_compatible_with_the_reference_output(tmp_path):
     second = open(files[1]).read().splitlines()
     assert second[0] == "DEPTH\tEXTRA" and second[1] == "M\tOHMM" and len(second) == 2 + table[::2].shape[0]
     assert model.save_results(None) is None
+
+
+def test_sliver_pass_of_the_half_ball_mesher():
+    """meshgen.half_ball_mesh(improve=N): the optional quality pass perturbs the free vertices of the worst tets and
+    re-triangulates.  The mesh must stay a valid input of the path (positive volumes, the same axis and boundary
+    vertices, every vertex used, consecutive axis vertices still joined by an edge where they were) with far fewer
+    slivers; improve=0 must reproduce the default mesh exactly."""
+    import numpy as np
+
+    from remo3d_b200 import meshgen
+    from remo3d_b200.mesh import Mesh
+
+    ez = np.array([-1.0, 0.0, 0.5])
+    kw = dict(h_electrode=0.06, h_axis=0.25, grading=0.5, h_max=6.0, seed=0)
+    m0 = meshgen.half_ball_mesh(50.0, ez, **kw)
+    m00 = meshgen.half_ball_mesh(50.0, ez, improve=0, **kw)
+    np.testing.assert_array_equal(m0["elems"], m00["elems"])
+    np.testing.assert_array_equal(m0["points"], m00["points"])
+    m1 = meshgen.half_ball_mesh(50.0, ez, improve=3, **kw)
+    q0, q1 = meshgen._quality(m0["points"], m0["elems"]), meshgen._quality(m1["points"], m1["elems"])
+    assert (q1 < 0.1).sum() * 3 <= (q0 < 0.1).sum()
+    x = m1["points"][m1["elems"]]
+    assert np.all(np.linalg.det(x[:, 1:] - x[:, :1]) > 0)
+    assert m1["points"].shape == m0["points"].shape and np.unique(m1["elems"]).size == m1["points"].shape[0]
+    fixed = (m0["points"][:, 1] == 0.0) | (np.linalg.norm(m0["points"], axis=1) >= 50.0 * (1 - 1e-6))
+    np.testing.assert_array_equal(m1["points"][fixed], m0["points"][fixed])  # axis, symmetry plane and sphere stay put
+    a0 = Mesh(m0["points"], m0["elems"], m0["mat"], m0["bfacets"], m0["bc"], m0["bc_names"]).axis_vertices()
+    a1 = Mesh(m1["points"], m1["elems"], m1["mat"], m1["bfacets"], m1["bc"], m1["bc_names"]).axis_vertices()
+    np.testing.assert_array_equal(a0, a1)
+    for z in ez:  # the electrodes are still mesh vertices
+        assert np.any((m1["points"][:, 0] == 0) & (m1["points"][:, 1] == 0) & (np.abs(m1["points"][:, 2] - z) < 1e-12))
