@@ -301,7 +301,7 @@ def half_ball_mesh(radius, electrodes_z, material=None, **kw):
     Morton curve for memory locality with the axis vertices kept as mesh vertices.  `material(centroids)`
     -> 0-based material index per tet (default: all 0)."""
     half = kw.get("half", True)
-    pts, n_axis, _ = half_ball_points(radius, electrodes_z, **{k: v for k, v in kw.items() if k not in ("improve", "improve_quality")})
+    pts, n_axis, _ = half_ball_points(radius, electrodes_z, **{k: v for k, v in kw.items() if k not in ("improve", "improve_quality", "improve_mode")})
     # Morton order with 21 bits per axis (locality of vertex numbers -> locality of CSR columns, at every
     # refinement level: the finest cells here are ~1e-4 of the domain)
     q = np.clip(((pts + radius) / (2 * radius) * (2 ** 21 - 1)).astype(np.uint64), 0, 2 ** 21 - 1)
@@ -335,13 +335,29 @@ def half_ball_mesh(radius, electrodes_z, material=None, **kw):
                 break
             x = pts[elems[bad]]
             h = np.sqrt(sum(((x[:, i] - x[:, j]) ** 2).sum(axis=1) for i in range(4) for j in range(i + 1, 4)) / 6.0)
-            hv = np.full(pts.shape[0], np.inf)
-            np.minimum.at(hv, elems[bad].ravel(), np.repeat(h, 4))
-            move = np.where(np.isfinite(hv) & ~fixed)[0]
-            if move.size == 0:
-                break
-            step = rng.standard_normal((move.size, 3))
-            step *= (0.18 * hv[move] / np.linalg.norm(step, axis=1))[:, None]
+            if kw.get("improve_mode", "normal") == "normal":
+                # a sliver's four points are nearly coplanar: push ONE free vertex of it out of that plane
+                c = x.mean(axis=1, keepdims=True)
+                _, _, vt = np.linalg.svd(x - c)
+                nrm = vt[:, 2, :]  # direction of least extent
+                free_v = ~fixed[elems[bad]]
+                has = free_v.any(axis=1)
+                pick = np.argmax(free_v, axis=1)
+                tv = elems[bad][np.arange(bad.size), pick][has]
+                d = ((x - c)[np.arange(bad.size), pick] * nrm).sum(axis=1)[has]
+                sgn = np.where(d >= 0, 1.0, -1.0)
+                move, first = np.unique(tv, return_index=True)
+                if move.size == 0:
+                    break
+                step = (sgn[first] * 0.3 * h[has][first])[:, None] * nrm[has][first]
+            else:
+                hv = np.full(pts.shape[0], np.inf)
+                np.minimum.at(hv, elems[bad].ravel(), np.repeat(h, 4))
+                move = np.where(np.isfinite(hv) & ~fixed)[0]
+                if move.size == 0:
+                    break
+                step = rng.standard_normal((move.size, 3))
+                step *= (0.18 * hv[move] / np.linalg.norm(step, axis=1))[:, None]
             pts = pts.copy()
             pts[move] += step
             if half:
