@@ -269,19 +269,8 @@ def _quality(points, elems):
     return vol / (e2 ** 1.5) * (6.0 * np.sqrt(2.0))
 
 
-def _delaunay_peeled(pts, on_plane, radius, seed):
-    """Delaunay tets of the cloud with the flat tets of the symmetry plane and the boundary slivers removed."""
-    from scipy.spatial import Delaunay
-
-    # Qhull is ~10x slower with thousands of exactly coplanar hull points (the symmetry plane):
-    # triangulate a copy whose plane points are lifted by <= 2e-11 R, keep the exact coordinates;
-    # the flat tets this creates on the plane are boundary slivers and are peeled below
-    lifted = pts.copy()
-    lifted[on_plane, 1] += np.random.default_rng(seed).uniform(0.0, 2e-11 * radius, size=int(on_plane.sum()))
-    tri = Delaunay(lifted)
-    elems = tri.simplices.astype(np.int32)
-    elems = elems[~on_plane[elems].all(axis=1)]  # exactly flat tets lying in the symmetry plane
-    # peel boundary slivers (flat tets between nearly coplanar hull points)
+def _peel(pts, elems):
+    """Remove boundary slivers (flat tets between nearly coplanar hull points)."""
     for _ in range(6):
         qual = _quality(pts, elems)
         _, owner = boundary_facets(elems, return_owner=True)
@@ -294,6 +283,69 @@ def _delaunay_peeled(pts, on_plane, radius, seed):
     return elems
 
 
+def _plane_lift(pts, on_plane, radius, seed):
+    """Qhull is ~10x slower with thousands of exactly coplanar hull points (the symmetry plane): it triangulates a copy
+    whose plane points are lifted by <= 2e-11 R (the exact coordinates are kept in the mesh); the flat tets this creates
+    in the plane are dropped.  Returns the lift of every point (0 off the plane)."""
+    lift = np.zeros(pts.shape[0])
+    lift[on_plane] = np.random.default_rng(seed).uniform(0.0, 2e-11 * radius, size=int(on_plane.sum()))
+    return lift
+
+
+def _delaunay(pts, lift, on_plane, ids=None):
+    """Delaunay tets of the points `ids` (all by default), global vertex numbers, without the flat tets of the plane."""
+    from scipy.spatial import Delaunay
+
+    sub = pts if ids is None else pts[ids]
+    lifted = sub.copy()
+    lifted[:, 1] += lift if ids is None else lift[ids]
+    simp = Delaunay(lifted).simplices
+    elems = (simp if ids is None else ids[simp]).astype(np.int32)
+    return elems[~on_plane[elems].all(axis=1)]
+
+
+def _delaunay_peeled(pts, on_plane, radius, seed, lift=None):
+    """Delaunay tets of the cloud with the flat tets of the symmetry plane and the boundary slivers removed."""
+    lift = _plane_lift(pts, on_plane, radius, seed) if lift is None else lift
+    return _peel(pts, _delaunay(pts, lift, on_plane))
+
+
+def _retriangulate_around(pts, lift, on_plane, on_hull, elems, moved, rings=3):
+    """Delaunay mesh after the vertices `moved` changed place, from the old mesh `elems`: only the tets around them are
+    replaced by the Delaunay tets of the surrounding sub-cloud (`rings` vertex rings).  The Delaunay triangulation of
+    points in general position is unique, so the patch fits the untouched rest exactly when the sub-cloud is wide enough;
+    this is CHECKED (every face in at most two tets, every face of a single tet on the domain boundary) and None is
+    returned when it does not hold, so the caller can triangulate the whole cloud instead."""
+    nv = pts.shape[0]
+    inner = np.zeros(nv, bool)
+    inner[moved] = True
+    inner[elems[inner[elems].any(axis=1)].ravel()] = True  # the moved vertices and their neighbours
+    region = inner[elems].any(axis=1)                       # old tets to replace: everything touching them
+    cloud = inner.copy()
+    for _ in range(rings - 1):
+        cloud[elems[cloud[elems].any(axis=1)].ravel()] = True
+    ids = np.flatnonzero(cloud)
+    if ids.size * 2 > nv:
+        return None  # not local any more
+    patch = _delaunay(pts, lift, on_plane, ids)
+    patch = patch[inner[patch].any(axis=1)]
+    new = np.concatenate([elems[~region], patch])
+    # validity of the union
+    faces = np.sort(np.concatenate([np.delete(new, i, axis=1) for i in range(4)], axis=0).astype(np.int64), axis=1)
+    order = np.lexsort((faces[:, 2], faces[:, 1], faces[:, 0]))
+    f = faces[order]
+    first = np.ones(f.shape[0], bool)
+    first[1:] = (f[1:] != f[:-1]).any(axis=1)
+    starts = np.flatnonzero(first)
+    cnt = np.diff(np.r_[starts, f.shape[0]])
+    if cnt.max() > 2:
+        return None
+    single = f[starts[cnt == 1]]
+    if not (on_plane[single].all(axis=1) | on_hull[single].all(axis=1) | (on_plane | on_hull)[single].all(axis=1)).all():
+        return None
+    return _peel(pts, new)
+
+
 def half_ball_mesh(radius, electrodes_z, material=None, **kw):
     """Graded half-ball (or full ball with half=False) tet mesh.
 
@@ -301,7 +353,7 @@ def half_ball_mesh(radius, electrodes_z, material=None, **kw):
     Morton curve for memory locality with the axis vertices kept as mesh vertices.  `material(centroids)`
     -> 0-based material index per tet (default: all 0)."""
     half = kw.get("half", True)
-    pts, n_axis, _ = half_ball_points(radius, electrodes_z, **{k: v for k, v in kw.items() if k not in ("improve", "improve_quality", "improve_mode")})
+    pts, n_axis, _ = half_ball_points(radius, electrodes_z, **{k: v for k, v in kw.items() if k not in ("improve", "improve_quality", "improve_mode", "improve_local")})
     # Morton order with 21 bits per axis (locality of vertex numbers -> locality of CSR columns, at every
     # refinement level: the finest cells here are ~1e-4 of the domain)
     q = np.clip(((pts + radius) / (2 * radius) * (2 ** 21 - 1)).astype(np.uint64), 0, 2 ** 21 - 1)
@@ -317,7 +369,8 @@ def half_ball_mesh(radius, electrodes_z, material=None, **kw):
     code = spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1)) | (spread(q[:, 2]) << np.uint64(2))
     pts = pts[np.argsort(code, kind="stable")]
     on_plane = pts[:, 1] == 0.0
-    elems = _delaunay_peeled(pts, on_plane, radius, kw.get("seed", 0) + 1)
+    lift = _plane_lift(pts, on_plane, radius, kw.get("seed", 0) + 1)
+    elems = _delaunay_peeled(pts, on_plane, radius, 0, lift=lift)
     # optional quality pass (off by default): Delaunay meshes of well-spaced points still hold SLIVERS (four nearly
     # coplanar, nearly cocircular points), and the slivers -- not the point spacing -- set the condition number the PCG
     # sees.  Vertices of the worst tets that are free to move (not on the axis, the symmetry plane or the sphere) are
@@ -326,7 +379,8 @@ def half_ball_mesh(radius, electrodes_z, material=None, **kw):
     if improve > 0:
         rng = np.random.default_rng(kw.get("seed", 0) + 7)
         qmin = float(kw.get("improve_quality", 0.12))
-        fixed = on_plane | ((pts[:, 0] == 0.0) & (pts[:, 1] == 0.0)) | (np.linalg.norm(pts, axis=1) >= radius * (1 - 1e-6))
+        on_hull = np.linalg.norm(pts, axis=1) >= radius * (1 - 1e-6)
+        fixed = on_plane | ((pts[:, 0] == 0.0) & (pts[:, 1] == 0.0)) | on_hull
         best = (int((_quality(pts, elems) < qmin).sum()), pts, elems)
         for it in range(improve):
             qual = _quality(pts, elems)
@@ -362,7 +416,8 @@ def half_ball_mesh(radius, electrodes_z, material=None, **kw):
             pts[move] += step
             if half:
                 pts[move, 1] = np.abs(pts[move, 1])  # stay on this side of the symmetry plane
-            elems = _delaunay_peeled(pts, on_plane, radius, kw.get("seed", 0) + 1 + it)
+            local = _retriangulate_around(pts, lift, on_plane, on_hull, elems, move) if kw.get("improve_local", True) else None
+            elems = local if local is not None else _delaunay_peeled(pts, on_plane, radius, 0, lift=lift)
             nbad = int((_quality(pts, elems) < qmin).sum())
             if nbad < best[0]:
                 best = (nbad, pts, elems)
