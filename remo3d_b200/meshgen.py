@@ -330,8 +330,11 @@ def _retriangulate_around(pts, lift, on_plane, on_hull, elems, moved, rings=3):
     patch = _delaunay(pts, lift, on_plane, ids)
     patch = patch[inner[patch].any(axis=1)]
     new = np.concatenate([elems[~region], patch])
-    # validity of the union
-    faces = np.sort(np.concatenate([np.delete(new, i, axis=1) for i in range(4)], axis=0).astype(np.int64), axis=1)
+    # validity of the union, checked on the tets that touch the sub-cloud (a mismatch can only sit there): every face in at
+    # most two tets; a face of a single tet is either a domain boundary face or on the outer rim of this sub-mesh, whose
+    # faces have no vertex in the sub-cloud
+    sub = new[cloud[new].any(axis=1)]
+    faces = np.sort(np.concatenate([np.delete(sub, i, axis=1) for i in range(4)], axis=0).astype(np.int64), axis=1)
     order = np.lexsort((faces[:, 2], faces[:, 1], faces[:, 0]))
     f = faces[order]
     first = np.ones(f.shape[0], bool)
@@ -341,9 +344,13 @@ def _retriangulate_around(pts, lift, on_plane, on_hull, elems, moved, rings=3):
     if cnt.max() > 2:
         return None
     single = f[starts[cnt == 1]]
-    if not (on_plane[single].all(axis=1) | on_hull[single].all(axis=1) | (on_plane | on_hull)[single].all(axis=1)).all():
+    bnd = on_plane | on_hull
+    if not (bnd[single].all(axis=1) | ~cloud[single].any(axis=1)).all():
         return None
-    return _peel(pts, new)
+    # boundary slivers can only have come back inside the patch
+    if ((bnd[patch].sum(axis=1) >= 3) & (_quality(pts, patch) < 2e-2)).any():
+        return _peel(pts, new)
+    return new
 
 
 def half_ball_mesh(radius, electrodes_z, material=None, **kw):
@@ -381,10 +388,14 @@ def half_ball_mesh(radius, electrodes_z, material=None, **kw):
         qmin = float(kw.get("improve_quality", 0.12))
         on_hull = np.linalg.norm(pts, axis=1) >= radius * (1 - 1e-6)
         fixed = on_plane | ((pts[:, 0] == 0.0) & (pts[:, 1] == 0.0)) | on_hull
-        best = (int((_quality(pts, elems) < qmin).sum()), pts, elems)
+        def rank_of(q):  # the PCG iteration count follows the WORST elements first, their number second
+            return (int((q < 0.01).sum()), int((q < 0.05).sum()), int((q < qmin).sum()))
+
+        best = (rank_of(_quality(pts, elems)), pts, elems)
         for it in range(improve):
             qual = _quality(pts, elems)
-            bad = np.where(qual < qmin)[0]
+            # late rounds concentrate on the worst elements (few vertices move: the re-triangulation stays local)
+            bad = np.where(qual < (qmin if it < 3 else 0.05))[0]
             if bad.size == 0:
                 break
             x = pts[elems[bad]]
@@ -394,16 +405,28 @@ def half_ball_mesh(radius, electrodes_z, material=None, **kw):
                 c = x.mean(axis=1, keepdims=True)
                 _, _, vt = np.linalg.svd(x - c)
                 nrm = vt[:, 2, :]  # direction of least extent
-                free_v = ~fixed[elems[bad]]
-                has = free_v.any(axis=1)
-                pick = np.argmax(free_v, axis=1)
+                # prefer a fully free vertex; failing that one of the symmetry plane (it then moves inside the plane)
+                semi = on_plane & ~on_hull & ~((pts[:, 0] == 0.0) & (pts[:, 1] == 0.0))
+                score = (~fixed[elems[bad]]) * 2 + semi[elems[bad]] * 1
+                has = score.max(axis=1) > 0
+                pick = np.argmax(score, axis=1)
                 tv = elems[bad][np.arange(bad.size), pick][has]
                 d = ((x - c)[np.arange(bad.size), pick] * nrm).sum(axis=1)[has]
                 sgn = np.where(d >= 0, 1.0, -1.0)
                 move, first = np.unique(tv, return_index=True)
                 if move.size == 0:
                     break
-                step = (sgn[first] * 0.3 * h[has][first])[:, None] * nrm[has][first]
+                dirn = sgn[first][:, None] * nrm[has][first]
+                inpl = semi[move]
+                if inpl.any():
+                    dp = dirn[inpl].copy()
+                    dp[:, 1] = 0.0
+                    weak = np.linalg.norm(dp, axis=1) < 0.3  # the sliver lies (almost) in the plane: any in-plane direction
+                    rnd = rng.standard_normal((int(weak.sum()), 3))
+                    rnd[:, 1] = 0.0
+                    dp[weak] = rnd
+                    dirn[inpl] = dp / np.linalg.norm(dp, axis=1)[:, None]
+                step = (0.3 * h[has][first])[:, None] * dirn
             else:
                 hv = np.full(pts.shape[0], np.inf)
                 np.minimum.at(hv, elems[bad].ravel(), np.repeat(h, 4))
@@ -415,12 +438,12 @@ def half_ball_mesh(radius, electrodes_z, material=None, **kw):
             pts = pts.copy()
             pts[move] += step
             if half:
-                pts[move, 1] = np.abs(pts[move, 1])  # stay on this side of the symmetry plane
+                pts[move, 1] = np.where(on_plane[move], 0.0, np.abs(pts[move, 1]))  # stay on this side of the symmetry plane
             local = _retriangulate_around(pts, lift, on_plane, on_hull, elems, move) if kw.get("improve_local", True) else None
             elems = local if local is not None else _delaunay_peeled(pts, on_plane, radius, 0, lift=lift)
-            nbad = int((_quality(pts, elems) < qmin).sum())
-            if nbad < best[0]:
-                best = (nbad, pts, elems)
+            sc = rank_of(_quality(pts, elems))
+            if sc < best[0]:
+                best = (sc, pts, elems)
         _, pts, elems = best
     # positive orientation
     x = pts[elems]
