@@ -427,6 +427,7 @@ def half_ball_mesh(radius, electrodes_z, material=None, **kw):
                     dp[weak] = rnd
                     dirn[inpl] = dp / np.linalg.norm(dp, axis=1)[:, None]
                 step = (0.3 * h[has][first])[:, None] * dirn
+                ymin = np.where(inpl, 0.0, 0.35 * h[has][first])  # off-plane vertices keep their distance from the plane
             else:
                 hv = np.full(pts.shape[0], np.inf)
                 np.minimum.at(hv, elems[bad].ravel(), np.repeat(h, 4))
@@ -435,11 +436,14 @@ def half_ball_mesh(radius, electrodes_z, material=None, **kw):
                     break
                 step = rng.standard_normal((move.size, 3))
                 step *= (0.18 * hv[move] / np.linalg.norm(step, axis=1))[:, None]
+                ymin = 0.35 * hv[move]
             pts = pts.copy()
             pts[move] += step
             if half:
-                pts[move, 1] = np.where(on_plane[move], 0.0, np.abs(pts[move, 1]))  # stay on this side of the symmetry plane
-            local = _retriangulate_around(pts, lift, on_plane, on_hull, elems, move) if kw.get("improve_local", True) else None
+                # stay on this side of the symmetry plane, and not so close to it that a flat boundary tet appears
+                pts[move, 1] = np.where(on_plane[move], 0.0, np.maximum(np.abs(pts[move, 1]), ymin))
+            # around a few hundred moved vertices the patch fits almost always; with thousands it rarely does (measured)
+            local = _retriangulate_around(pts, lift, on_plane, on_hull, elems, move) if (kw.get("improve_local", True) and move.size <= 300) else None
             elems = local if local is not None else _delaunay_peeled(pts, on_plane, radius, 0, lift=lift)
             sc = rank_of(_quality(pts, elems))
             if sc < best[0]:
