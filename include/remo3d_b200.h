@@ -66,9 +66,12 @@ int remo_mesh_set(void* ctx, int dim, int64_t nv, const double* xyz, int64_t nt,
                   const int32_t* mat, int64_t nb, const int32_t* bfacets, const uint8_t* bdirichlet,
                   int64_t naxis, const int32_t* axis_vertices);
 
-/* Symbolic phase: topology, dof numbering, Dirichlet dofs, CSR pattern
+/* Symbolic phase: topology, dof numbering, Dirichlet dofs, dof -> element adjacency
  * (replaces `fes = ngs.H1(mesh, order=3, dirichlet=..)`, ngsolve_functions.py:27, and the
- * sparsity-graph part of `a.Assemble()`, :47).  order in {1,2,3}.                              */
+ * sparsity-graph part of `a.Assemble()`, :47).  order in {1,2,3}.
+ * The CSR pattern itself is built on demand (remo_matrix_nnz / remo_matrix_get / a solve that
+ * reads the assembled matrix): the element-wise PCG path of order-2 tets never needs it.  *nnz is
+ * 0 unless the pattern exists when the call returns (remo_set_option("lazy_matrix", 0): always). */
 int remo_space_build(void* ctx, int order, int64_t* ndof, int64_t* nnz, int64_t* nedges, int64_t* nfaces);
 
 /* Numbering export for parity tests: edges ne x 2, faces nf x 3 (sorted vertex tuples),
@@ -79,12 +82,23 @@ int remo_topology_get(void* ctx, int32_t* edges, int32_t* faces, int32_t* elem_e
  * (ngsolve_functions.py:31-36, 47).  sigma: nmat doubles, one per material (worker.py:101).    */
 int remo_assemble(void* ctx, int nmat, const double* sigma);
 
-/* Export the assembled matrix, CSR with sorted columns, Dirichlet rows kept (reference numbering). */
+/* Numeric assembly ... with "lazy_matrix" (default) remo_assemble evaluates the element metrics only; the CSR
+ * values are gathered row by row (atomic-free, bit-reproducible) when first needed.
+ * Export the assembled matrix, CSR with sorted columns, Dirichlet rows kept (reference numbering). */
 int remo_matrix_get(void* ctx, int64_t* rowptr, int32_t* col, double* val);
+/* Non-zeros of the CSR pattern (builds the pattern if it does not exist yet).                   */
+int remo_matrix_nnz(void* ctx, int64_t* nnz);
 int remo_dirichlet_get(void* ctx, uint8_t* constrained);
 
 /* `c = ngs.Preconditioner(a, "local"|"multigrid")` (ngsolve_functions.py:46).                  */
 int remo_precond_setup(void* ctx, int kind);
+
+/* Parity export of what remo_precond_setup built (every pointer may be NULL): dinv = ndof doubles, 1 / a_ii on free dofs and
+ * 0 on constrained ones; the vertex block of A (= P1 stiffness matrix, level 0 of the "multigrid" V-cycle) as CSR with
+ * nv + 1 row pointers and nv + 2 * nedges entries; *nlevels in = capacity of level_rows / level_nnz, out = levels of the
+ * aggregation hierarchy (0 for "local").                                                                              */
+int remo_precond_get(void* ctx, double* dinv, int64_t* vv_rowptr, int32_t* vv_col, double* vv_val, int* nlevels,
+                     int64_t* level_rows, int64_t* level_nnz);
 
 /* Right-hand sides: AddPointSource for every (rhs, source) pair (ngsolve_functions.py:10-21, 39-44).
  * src_ptr: nrhs+1 offsets into src_z / src_fac.  1 <= nrhs <= REMO_MAX_RHS.                    */

@@ -28,8 +28,10 @@ SIGNATURES = {
     "remo_topology_get": (C.c_int, [_p, _p, _p, _p, _p]),
     "remo_assemble": (C.c_int, [_p, C.c_int, _p]),
     "remo_matrix_get": (C.c_int, [_p, _p, _p, _p]),
+    "remo_matrix_nnz": (C.c_int, [_p, _i64p]),
     "remo_dirichlet_get": (C.c_int, [_p, _p]),
     "remo_precond_setup": (C.c_int, [_p, C.c_int]),
+    "remo_precond_get": (C.c_int, [_p, _p, _p, _p, _p, C.POINTER(C.c_int), _p, _p]),
     "remo_rhs_point_sources": (C.c_int, [_p, C.c_int, _p, _p, _p]),
     "remo_rhs_get": (C.c_int, [_p, C.c_int, _p]),
     "remo_solve": (C.c_int, [_p, C.c_double, C.c_int, _p, _p]),
@@ -92,7 +94,8 @@ class Context:
             raise RemoError(rc, (self.lib.remo_last_error(None) or b"").decode())
         self.h = h
         self.device = int(device)
-        self.ndof = self.nnz = self.ne = self.nf = 0
+        self.ndof = self.ne = self.nf = 0
+        self._nnz = 0
         self.nrhs = 0
         self.order = 0
 
@@ -132,9 +135,19 @@ class Context:
     def space_build(self, order):
         out = [C.c_int64() for _ in range(4)]
         self._ck(self.lib.remo_space_build(self.h, int(order), *[C.byref(o) for o in out]))
-        self.ndof, self.nnz, self.ne, self.nf = (o.value for o in out)
+        self.ndof, self._nnz, self.ne, self.nf = (o.value for o in out)
         self.order = int(order)
-        return self.ndof, self.nnz
+        return self.ndof, self._nnz
+
+    @property
+    def nnz(self):
+        """Non-zeros of the CSR pattern.  The pattern is built on demand (the element-wise PCG path never needs it), so
+        the first read after `space_build` may cost a kernel pass."""
+        if not self._nnz and self.ndof:
+            n = C.c_int64()
+            self._ck(self.lib.remo_matrix_nnz(self.h, C.byref(n)))
+            self._nnz = n.value
+        return self._nnz
 
     def topology(self):
         nle = 6 if self.dim == 3 else 3
@@ -163,6 +176,19 @@ class Context:
 
     def precond_setup(self, kind):
         self._ck(self.lib.remo_precond_setup(self.h, PRECOND[kind] if isinstance(kind, str) else int(kind)))
+
+    def precond_get(self, vertex_block=False):
+        """(dinv, vertex block CSR or None, [(rows, nnz) per level of the aggregation hierarchy]) -- parity export."""
+        dinv = np.empty(self.ndof, np.float64)
+        nlev = C.c_int(16)
+        rows, nnzs = np.zeros(16, np.int64), np.zeros(16, np.int64)
+        vv = None
+        if vertex_block:
+            n = self.nv + 2 * self.ne
+            vv = (np.empty(self.nv + 1, np.int64), np.empty(n, np.int32), np.empty(n, np.float64))
+        self._ck(self.lib.remo_precond_get(self.h, _ptr(dinv), *([_ptr(a) for a in vv] if vv else [None, None, None]), C.byref(nlev),
+                                            _ptr(rows), _ptr(nnzs)))
+        return dinv, vv, [(int(rows[l]), int(nnzs[l])) for l in range(nlev.value)]
 
     # ---- right-hand sides / solve / sampling
     def rhs_point_sources(self, src_ptr, src_z, src_fac):

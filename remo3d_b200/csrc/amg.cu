@@ -9,11 +9,17 @@
 //     leading nv x nv block of A (no second assembly, prolongation = injection);
 //   * z = M r :  z_high = D^-1 r_high  (Jacobi on the edge / face dofs, whose block is well conditioned), and
 //                z_vert = V-cycle(A_vv) r_vert;
-//   * the V-cycle hierarchy is built on the GPU by plain aggregation: vertices are ranked along a Morton curve of
-//     their coordinates and every 8 consecutive ranks form an aggregate (coarse levels: 8 consecutive rows), the
-//     coarse operators are Galerkin products with piecewise-constant prolongation (sort + reduce-by-key), the
-//     coarsest level (<= 256 rows) is inverted densely.  Smoother: l1-Jacobi (always a contraction), symmetric cycle,
-//     coarse correction over-weighted by 1.5 (plain aggregation under-corrects) -> M is SPD and plain PCG applies.
+//   * the V-cycle hierarchy is built on the GPU by STRENGTH-BASED PAIRWISE aggregation: per level `amg_passes` (3)
+//     passes of "every unmatched row points at its strongest unmatched neighbour (strength -a_ij / sqrt(a_ii a_jj),
+//     ties to the smaller index); mutual pointers become a pair" (`amg_rounds` handshake rounds per pass, rows left over
+//     stay single), each pass followed by the Galerkin product of the pair map (sort + reduce-by-key), so an aggregate
+//     has at most 2^passes rows and follows the strong couplings -- across the 1:100 conductivity jumps and along the
+//     anisotropy of the graded mesh -- instead of cutting them the way the geometric (Morton-rank) aggregates of round 1
+//     did: 155 -> 119 PCG iterations on the 200 k-dof bench mesh, 105 with an exact P1 solve
+//     (tools/precond_study/amg_variants.py).  `remo_set_option("amg_agg", 0)` restores the Morton aggregates.
+//     Prolongation piecewise constant, the coarsest level (<= 256 rows) is inverted densely.  Smoother: l1-Jacobi
+//     (always a contraction), symmetric cycle, coarse correction over-weighted by 1.5 (plain aggregation
+//     under-corrects) -> M is SPD and plain PCG applies.
 // Everything works on row-major n x nrhs blocks, like the PCG.
 #include <cub/cub.cuh>
 
@@ -34,56 +40,123 @@ double env_d(const char* name, double def) {
   return e ? atof(e) : def;
 }
 
-// ---------------------------------------------------------------- level 0 = free-free part of the vertex block
-__global__ void k_vv_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                           const uint8_t* __restrict__ con, int64_t nv, int32_t* __restrict__ cnt) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= nv) return;
-  int n = 0;
-  const bool ci = con[i];
-  for (int64_t j = rowptr[i]; j < rowptr[i + 1]; j++) {
-    const int32_t c = col[j];
-    if (c >= nv) break;  // columns ascending: vertex dofs first
-    if (c == i || (!ci && !con[c])) n++;
-  }
-  cnt[i] = n;
-}
-
-__global__ void k_vv_fill(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
-                          const uint8_t* __restrict__ con, int64_t nv, const int64_t* __restrict__ rp0,
-                          int32_t* __restrict__ col0, double* __restrict__ val0) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= nv) return;
-  int64_t o = rp0[i];
-  const bool ci = con[i];
-  for (int64_t j = rowptr[i]; j < rowptr[i + 1]; j++) {
-    const int32_t c = col[j];
-    if (c >= nv) break;
-    if (c == i || (!ci && !con[c])) { col0[o] = c; val0[o] = val[j]; o++; }
-  }
-}
-
-__global__ void k_excl_to_ptr(const int32_t* __restrict__ incl, int64_t n, int64_t* __restrict__ ptr) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i > n) return;
-  ptr[i] = (i == 0) ? 0 : (int64_t)incl[i - 1];
-}
-
 // smoother diagonal: l1-Jacobi, dinv_i = 1 / sum_j |a_ij|.  D_l1 - A is diagonally dominant with a non-negative
 // diagonal, hence positive semi-definite: the sweep x += dinv (b - A x) is a contraction in the A-norm for any SPD A
 // (no global eigenvalue estimate needed, robust on sliver elements), and the symmetric V-cycle is SPD.
 // dinv = 0 marks rows outside the coarse space (constrained vertices, empty aggregates).
 __global__ void k_level_dinv(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
-                             const uint8_t* __restrict__ con, int64_t n, double* __restrict__ dinv) {
+                             const uint8_t* __restrict__ con, int64_t n, double* __restrict__ dinv, double* __restrict__ diag) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   double d = 0.0, l1 = 0.0;
   if (!(con && con[i]))
     for (int64_t j = rowptr[i]; j < rowptr[i + 1]; j++) {
+      const int32_t cj = col[j];
+      if (con && con[cj] && cj != (int32_t)i) continue;  // couplings to constrained vertices (their x is always 0)
       l1 += fabs(val[j]);
-      if (col[j] == (int32_t)i) d = val[j];
+      if (cj == (int32_t)i) d = val[j];
     }
   dinv[i] = d > 0.0 ? 1.0 / l1 : 0.0;
+  if (diag) diag[i] = d > 0.0 ? d : 0.0;
+}
+
+// ---------------------------------------------------------------- pairwise aggregation (handshake matching)
+// match[i]: -2 = not part of the coarse space (constrained / empty row), -1 = unmatched, >= 0 = partner row
+__global__ void k_pair_init(const double* __restrict__ diag, int64_t n, int32_t* __restrict__ match) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) match[i] = diag[i] > 0.0 ? -1 : -2;
+}
+
+// 8 lanes per row: strongest unmatched neighbour (only negative off-diagonals couple; ties -> smaller column)
+__global__ void __launch_bounds__(TB) k_pair_pick(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                  const double* __restrict__ val, const double* __restrict__ diag,
+                                                  const int32_t* __restrict__ match, int64_t n, int32_t* __restrict__ pick) {
+  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
+  const int l8 = threadIdx.x & 7;
+  double bw = 0.0;
+  int32_t bj = -1;
+  const bool live = row < n && match[row] == -1;
+  if (live) {
+    const double di = diag[row];
+    for (int64_t j = rowptr[row] + l8; j < rowptr[row + 1]; j += 8) {
+      const int32_t cj = col[j];
+      const double a = val[j];
+      if (cj == (int32_t)row || !(a < 0.0) || match[cj] != -1) continue;
+      const double w = -a / sqrt(di * diag[cj]);
+      if (w > bw || (w == bw && bj >= 0 && cj < bj)) { bw = w; bj = cj; }
+    }
+  }
+#pragma unroll
+  for (int o = 4; o; o >>= 1) {
+    const double ow = __shfl_xor_sync(0xffffffffu, bw, o);
+    const int32_t oj = __shfl_xor_sync(0xffffffffu, bj, o);
+    if (oj >= 0 && (ow > bw || (ow == bw && (bj < 0 || oj < bj)))) { bw = ow; bj = oj; }
+  }
+  if (row < n && l8 == 0) pick[row] = live ? bj : -1;
+}
+
+__global__ void k_pair_match(const int32_t* __restrict__ pick, int64_t n, int32_t* __restrict__ match) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n || match[i] != -1) return;
+  const int32_t j = pick[i];
+  if (j >= 0 && pick[j] == (int32_t)i) match[i] = j;
+}
+
+// leaders: single rows and the smaller row of every pair
+__global__ void k_pair_flags(const int32_t* __restrict__ match, int64_t n, int32_t* __restrict__ flag) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t m = match[i];
+  flag[i] = (m == -1 || (m >= 0 && (int32_t)i < m)) ? 1 : 0;
+}
+
+__global__ void k_pair_ids(const int32_t* __restrict__ match, const int32_t* __restrict__ incl, int64_t n, int32_t* __restrict__ id) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t m = match[i];
+  id[i] = (m == -2) ? -1 : ((m == -1 || (int32_t)i < m) ? incl[i] - 1 : incl[m] - 1);
+}
+
+// fallback when a pass hardly coarsens: groups of `g` consecutive live rows
+__global__ void k_live_flags(const double* __restrict__ diag, int64_t n, int32_t* __restrict__ flag) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = diag[i] > 0.0 ? 1 : 0;
+}
+__global__ void k_block_ids(const int32_t* __restrict__ flag, const int32_t* __restrict__ incl, int64_t n, int g, int32_t* __restrict__ id) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) id[i] = flag[i] ? (incl[i] - 1) / g : -1;
+}
+
+// tot[i] = id[tot[i]]  (composition of the pass maps; -1 stays -1)
+__global__ void k_compose(int32_t* __restrict__ tot, const int32_t* __restrict__ id, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) { const int32_t t = tot[i]; tot[i] = t >= 0 ? id[t] : -1; }
+}
+
+__global__ void k_diag_of(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val, int64_t n,
+                          double* __restrict__ diag) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double d = 0.0;
+  for (int64_t j = rowptr[i]; j < rowptr[i + 1]; j++)
+    if (col[j] == (int32_t)i) d = val[j];
+  diag[i] = d > 0.0 ? d : 0.0;
+}
+
+__global__ void k_agg_keys(const int32_t* __restrict__ agg, int64_t n, uint32_t* __restrict__ key, int32_t* __restrict__ row) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) { key[i] = (uint32_t)agg[i]; row[i] = (int32_t)i; }  // -1 -> 0xffffffff sorts behind every aggregate
+}
+
+__global__ void k_agg_ptr(const uint32_t* __restrict__ skey, int64_t n, int64_t nc, int32_t* __restrict__ ptr) {
+  int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (a > nc) return;
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (skey[mid] < (uint32_t)a) lo = mid + 1; else hi = mid;
+  }
+  ptr[a] = (int32_t)lo;
 }
 
 // ---------------------------------------------------------------- Morton ranks of the vertices
@@ -112,32 +185,29 @@ __global__ void k_morton(const double* __restrict__ xyz, int64_t nv, int dim, co
   idx[i] = (uint32_t)i;
 }
 
-// perm = vertices in Morton order -> aggregate of vertex perm[p] is p / AGG; members row-major (AGG per aggregate)
-__global__ void k_agg_from_perm(const uint32_t* __restrict__ perm, int64_t n, int32_t* __restrict__ agg, int32_t* __restrict__ members,
-                                int64_t npad) {
+// perm = vertices in Morton order -> aggregate of vertex perm[p] is p / AGG  (amg_agg = 0: the round-1 aggregates)
+__global__ void k_agg_from_perm(const uint32_t* __restrict__ perm, int64_t n, int32_t* __restrict__ agg) {
   int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (p >= npad) return;
-  if (p < n) {
-    agg[perm[p]] = (int32_t)(p / AGG);
-    members[p] = (int32_t)perm[p];
-  } else {
-    members[p] = -1;
-  }
+  if (p < n) agg[perm[p]] = (int32_t)(p / AGG);
+}
+__global__ void k_agg_consecutive(int64_t n, int32_t* __restrict__ agg) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) agg[i] = (int32_t)(i / AGG);
 }
 
 // ---------------------------------------------------------------- Galerkin coarse operator, piecewise-constant P
 __global__ void k_galerkin_pairs(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
-                                 const int32_t* __restrict__ agg, const double* __restrict__ dinv, int64_t n,
+                                 const int32_t* __restrict__ agg, const double* __restrict__ dinv, int64_t n, uint64_t nc,
                                  uint64_t* __restrict__ keys, double* __restrict__ vals) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint64_t ai = agg ? (uint64_t)agg[i] : (uint64_t)(i / AGG);
-  const bool dead_i = dinv[i] == 0.0;  // constrained or empty row: not part of the coarse space
+  const int32_t ai = agg[i];
+  const bool dead_i = ai < 0 || dinv[i] == 0.0;  // constrained or empty row: not part of the coarse space
   for (int64_t j = rowptr[i]; j < rowptr[i + 1]; j++) {
     const int32_t c = col[j];
-    const bool dead = dead_i || dinv[c] == 0.0;
-    const uint64_t ac = agg ? (uint64_t)agg[c] : (uint64_t)(c / AGG);
-    keys[j] = dead ? ~0ull : ((ai << 32) | ac);
+    const int32_t ac = agg[c];
+    const bool dead = dead_i || ac < 0 || dinv[c] == 0.0;
+    keys[j] = dead ? (nc << 32) : (((uint64_t)(uint32_t)ai << 32) | (uint32_t)ac);  // dropped entries sort behind every row
     vals[j] = dead ? 0.0 : val[j];
   }
 }
@@ -216,18 +286,15 @@ __global__ void k_jacobi0(const double* __restrict__ dinv, const double* __restr
   X[e] = omega * dinv[e / k] * B[e];
 }
 
-__global__ void k_restrict(const int32_t* __restrict__ members, const double* __restrict__ R, double* __restrict__ BC, int k,
-                           int64_t n, int64_t nc) {
+// rows of an aggregate in ascending order (members / aggptr): fixed summation order -> bit-reproducible
+__global__ void k_restrict(const int32_t* __restrict__ aggptr, const int32_t* __restrict__ members, const double* __restrict__ R,
+                           double* __restrict__ BC, int k, int64_t nc) {
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= nc * k) return;
   const int64_t a = e / k;
   const int r = (int)(e - a * k);
   double s = 0.0;
-#pragma unroll
-  for (int m = 0; m < AGG; m++) {
-    int64_t i = members ? (int64_t)members[a * AGG + m] : a * AGG + m;
-    if (i >= 0 && i < n) s += R[i * k + r];
-  }
+  for (int32_t p = aggptr[a]; p < aggptr[a + 1]; p++) s += R[(int64_t)members[p] * k + r];
   BC[e] = s;
 }
 
@@ -237,9 +304,9 @@ __global__ void k_prolong(const int32_t* __restrict__ agg, const double* __restr
   if (e >= n * k) return;
   const int64_t i = e / k;
   const int r = (int)(e - i * k);
-  if (dinv[i] == 0.0) return;  // constrained / empty rows stay zero
-  const int64_t a = agg ? (int64_t)agg[i] : i / AGG;
-  X[e] = fma(alpha, XC[a * k + r], X[e]);
+  const int32_t a = agg[i];
+  if (a < 0 || dinv[i] == 0.0) return;  // constrained / empty rows stay zero
+  X[e] = fma(alpha, XC[(int64_t)a * k + r], X[e]);
 }
 
 // ---------------------------------------------------------------- coarsest level: dense inverse
@@ -332,99 +399,186 @@ void spmm_smooth(Ctx* c, const int64_t* rowptr, const int32_t* col, const double
 void amg_release(Ctx* c) {
   cudaStream_t s = c->stream;
   for (auto& L : c->amg) {
-    L.rowptr.release(s); L.col.release(s); L.val.release(s); L.dinv.release(s); L.agg.release(s); L.members.release(s);
-    L.b.release(s); L.x.release(s); L.t.release(s);
+    L.rowptr.release(s); L.col.release(s); L.val.release(s); L.dinv.release(s); L.diag.release(s); L.agg.release(s);
+    L.members.release(s); L.aggptr.release(s); L.b.release(s); L.x.release(s); L.t.release(s);
   }
   c->amg.clear();
+  for (auto& T : c->amg_tmp) { T.rowptr.release(s); T.col.release(s); T.val.release(s); T.diag.release(s); }
+  for (auto& w : c->amg_w) w.release(s);
   c->amg_dense.release(s);
   c->amg_nrhs = 0;
   c->amg_nlev = 0;
 }
 
-// The level objects (and all temporaries, scratch slots of the context) persist across meshes: setup only grows buffers.
-void amg_setup(Ctx* c) {
-  cudaStream_t st = c->stream;
-  const int64_t nv = c->nv;
-  if (c->amg.capacity() < MAXLEV) c->amg.reserve(MAXLEV);
-  if (c->amg.empty()) c->amg.emplace_back();
-  int nlev = 1;
+namespace {
+
+struct CsrRef {
+  int64_t n, nnz;
+  const int64_t* rowptr;
+  const int32_t* col;
+  const double* val;
+  const double* diag;  // > 0 on the rows that belong to the coarse space
+};
+
+int bits_of(uint64_t v) {
+  int b = 1;
+  while (b < 64 && (v >> b)) b++;
+  return b;
+}
+
+int32_t inclusive_scan_total(Ctx* c, const int32_t* in, int32_t* out, int64_t n) {
   size_t bytes = 0;
-  {
-    // ---- level 0: free-free part of the leading nv x nv block
-    Ctx::AmgLevel& L = c->amg[0];
-    L.n = nv;
-    int32_t* cnt = scratch<int32_t>(c, 4, nv);
-    int32_t* incl = scratch<int32_t>(c, 5, nv);
-    LAUNCH(c, k_vv_count, grid_for(nv, TB), TB, 0, c->rowptr.p, c->col.p, c->constrained.p, nv, cnt);
-    CK(cub::DeviceScan::InclusiveSum(nullptr, bytes, cnt, incl, nv, st));
-    c->tmp.ensure(bytes, st);
-    CK(cub::DeviceScan::InclusiveSum(c->tmp.p, bytes, cnt, incl, nv, st));
-    c->launches += 2;
-    int32_t total = 0;
-    CK(cudaMemcpyAsync(&total, incl + (nv - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  cudaStream_t st = c->stream;
+  CK(cub::DeviceScan::InclusiveSum(nullptr, bytes, in, out, n, st));
+  c->tmp.ensure(bytes, st);
+  CK(cub::DeviceScan::InclusiveSum(c->tmp.p, bytes, in, out, n, st));
+  c->launches += 2;
+  int32_t total = 0;
+  CK(cudaMemcpyAsync(&total, out + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return total;
+}
+
+// Galerkin product P^T A P with the piecewise-constant prolongation of the row -> coarse row map `agg` (-1 = dropped):
+// (coarse row, coarse column) keys of every entry, radix sort, reduce-by-key -> coarse CSR.  Returns its nnz.
+int64_t galerkin(Ctx* c, const CsrRef& F, const int32_t* agg, int64_t nc, DBuf<int64_t>& rowptr, DBuf<int32_t>& col, DBuf<double>& val) {
+  cudaStream_t st = c->stream;
+  size_t bytes = 0;
+  uint64_t* keys = scratch<uint64_t>(c, 0, F.nnz);
+  uint64_t* keys2 = scratch<uint64_t>(c, 1, F.nnz);
+  uint64_t* ukeys = scratch<uint64_t>(c, 6, F.nnz);
+  double* vals = scratch<double>(c, 2, F.nnz);
+  double* vals2 = scratch<double>(c, 3, F.nnz);
+  double* uvals = scratch<double>(c, 7, F.nnz);
+  int64_t* nruns = scratch<int64_t>(c, 9, 2);
+  LAUNCH(c, k_galerkin_pairs, grid_for(F.n, TB), TB, 0, F.rowptr, F.col, F.val, agg, F.diag, F.n, (uint64_t)nc, keys, vals);
+  const int end_bit = std::min(64, 32 + bits_of((uint64_t)nc));  // dropped entries carry the key nc << 32
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys, keys2, vals, vals2, F.nnz, 0, end_bit, st));
+  c->tmp.ensure(bytes, st);
+  CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, keys, keys2, vals, vals2, F.nnz, 0, end_bit, st));
+  CK(cub::DeviceReduce::ReduceByKey(nullptr, bytes, keys2, ukeys, vals2, uvals, nruns, cub::Sum(), F.nnz, st));
+  c->tmp.ensure(bytes, st);
+  CK(cub::DeviceReduce::ReduceByKey(c->tmp.p, bytes, keys2, ukeys, vals2, uvals, nruns, cub::Sum(), F.nnz, st));
+  c->launches += 8;
+  int64_t hr = 0;
+  uint64_t lastkey = 0;
+  CK(cudaMemcpyAsync(&hr, nruns, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (hr > 0) {
+    CK(cudaMemcpyAsync(&lastkey, ukeys + (hr - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    L.nnz = total;
-    L.rowptr.ensure(nv + 1, st); L.col.ensure(total, st); L.val.ensure(total, st); L.dinv.ensure(nv, st);
-    LAUNCH(c, k_excl_to_ptr, grid_for(nv + 1, TB), TB, 0, incl, nv, L.rowptr.p);
-    LAUNCH(c, k_vv_fill, grid_for(nv, TB), TB, 0, c->rowptr.p, c->col.p, c->val.p, c->constrained.p, nv, L.rowptr.p, L.col.p, L.val.p);
-    LAUNCH(c, k_level_dinv, grid_for(nv, TB), TB, 0, L.rowptr.p, L.col.p, L.val.p, c->constrained.p, nv, L.dinv.p);
-    // ---- aggregates of level 0 from the Morton ranks of the vertex coordinates
-    const double* lohi = mesh_bbox(c);
-    uint64_t* code = scratch<uint64_t>(c, 0, nv);
-    uint64_t* codes = scratch<uint64_t>(c, 1, nv);
-    uint32_t* idx = scratch<uint32_t>(c, 2, nv);
-    uint32_t* perm = scratch<uint32_t>(c, 3, nv);
-    LAUNCH(c, k_morton, grid_for(nv, TB), TB, 0, c->xyz.p, nv, c->dim, lohi, code, idx);
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, code, codes, idx, perm, nv, 0, 63, st));
-    c->tmp.ensure(bytes, st);
-    CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, code, codes, idx, perm, nv, 0, 63, st));
-    c->launches += 4;
-    const int64_t nc = (nv + AGG - 1) / AGG;
-    L.agg.ensure(nv, st); L.members.ensure(nc * AGG, st);
-    LAUNCH(c, k_agg_from_perm, grid_for(nc * AGG, TB), TB, 0, perm, nv, L.agg.p, L.members.p, nc * AGG);
+    if ((lastkey >> 32) >= (uint64_t)nc) hr--;  // the run of dropped (constrained) entries
   }
+  rowptr.ensure(nc + 1, st); col.ensure(std::max<int64_t>(hr, 1), st); val.ensure(std::max<int64_t>(hr, 1), st);
+  LAUNCH(c, k_coarse_rowptr, grid_for(nc + 1, TB), TB, 0, ukeys, hr, nc, rowptr.p);
+  if (hr) {
+    LAUNCH(c, k_coarse_cols, grid_for(hr, TB), TB, 0, ukeys, hr, col.p);
+    CK(cudaMemcpyAsync(val.p, uvals, hr * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  }
+  return hr;
+}
+
+// Pairwise aggregation of level F: fills F.agg (row -> coarse row, -1 = not in the coarse space) and the coarse level's
+// CSR (the Galerkin product of the last pass IS the coarse operator).  Returns the number of coarse rows.
+int64_t aggregate_pairwise(Ctx* c, Ctx::AmgLevel& F, Ctx::AmgLevel& C) {
+  cudaStream_t st = c->stream;
+  CsrRef cur{F.n, F.nnz, F.rowptr.p, F.col.p, F.val.p, F.diag.p};
+  const int passes = std::max(1, c->amg_passes), rounds = std::max(1, c->amg_rounds);
+  int64_t nc = 0;
+  for (int p = 0; p < passes; p++) {
+    const int64_t n = cur.n;
+    for (auto& w : c->amg_w) w.ensure(n, st);
+    int32_t *match = c->amg_w[0].p, *pick = c->amg_w[1].p, *flag = c->amg_w[2].p, *incl = c->amg_w[3].p, *id = c->amg_w[4].p;
+    LAUNCH(c, k_pair_init, grid_for(n, TB), TB, 0, cur.diag, n, match);
+    for (int r = 0; r < rounds; r++) {
+      LAUNCH(c, k_pair_pick, grid_for(n * 8, TB), TB, 0, cur.rowptr, cur.col, cur.val, cur.diag, match, n, pick);
+      LAUNCH(c, k_pair_match, grid_for(n, TB), TB, 0, pick, n, match);
+    }
+    LAUNCH(c, k_pair_flags, grid_for(n, TB), TB, 0, match, n, flag);
+    nc = inclusive_scan_total(c, flag, incl, n);
+    if (nc > (int64_t)(0.8 * (double)n) && n > COARSEST) {
+      // the strength graph hardly matched anything (no negative couplings left): pairs of consecutive live rows
+      LAUNCH(c, k_live_flags, grid_for(n, TB), TB, 0, cur.diag, n, flag);
+      const int64_t live = inclusive_scan_total(c, flag, incl, n);
+      nc = (live + 1) / 2;
+      LAUNCH(c, k_block_ids, grid_for(n, TB), TB, 0, flag, incl, n, 2, id);
+    } else {
+      LAUNCH(c, k_pair_ids, grid_for(n, TB), TB, 0, match, incl, n, id);
+    }
+    if (nc < 1) FAIL(REMO_ERR_MESH, "amg_setup: no unconstrained vertex is left on level with %lld rows", (long long)n);
+    if (p == 0) CK(cudaMemcpyAsync(F.agg.p, id, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    else LAUNCH(c, k_compose, grid_for(F.n, TB), TB, 0, F.agg.p, id, F.n);
+    const bool last = (p == passes - 1) || nc <= COARSEST;
+    if (last) {
+      C.nnz = galerkin(c, cur, id, nc, C.rowptr, C.col, C.val);
+      break;
+    }
+    Ctx::AmgTmp& T = c->amg_tmp[p & 1];
+    T.n = nc;
+    T.nnz = galerkin(c, cur, id, nc, T.rowptr, T.col, T.val);
+    T.diag.ensure(nc, st);
+    LAUNCH(c, k_diag_of, grid_for(nc, TB), TB, 0, T.rowptr.p, T.col.p, T.val.p, nc, T.diag.p);
+    cur = CsrRef{T.n, T.nnz, T.rowptr.p, T.col.p, T.val.p, T.diag.p};
+  }
+  return nc;
+}
+
+}  // namespace
+
+// Level 0 (rowptr / col / val / dinv / diag of c->amg[0], n = nv) must be in place: builds the coarser levels.
+// The level objects (and all temporaries, scratch slots of the context) persist across meshes: setup only grows buffers.
+void amg_build_hierarchy(Ctx* c) {
+  cudaStream_t st = c->stream;
+  size_t bytes = 0;
+  int nlev = 1;
   // ---- coarser levels by Galerkin products until the level is small enough for a dense inverse
   while (c->amg[nlev - 1].n > COARSEST && nlev < MAXLEV) {
     if ((int)c->amg.size() <= nlev) c->amg.emplace_back();
     Ctx::AmgLevel& F = c->amg[nlev - 1];
     Ctx::AmgLevel& C = c->amg[nlev];
-    nlev++;
-    const int64_t nc = (F.n + AGG - 1) / AGG;
+    F.agg.ensure(F.n, st);
+    int64_t nc = 0;
+    if (c->amg_agg != 0) {
+      nc = aggregate_pairwise(c, F, C);
+    } else {
+      // round-1 aggregates: 8 consecutive Morton ranks of the vertex coordinates on level 0, 8 consecutive rows below
+      nc = (F.n + AGG - 1) / AGG;
+      if (nlev == 1) {
+        const double* lohi = mesh_bbox(c);
+        uint64_t* code = scratch<uint64_t>(c, 0, F.n);
+        uint64_t* codes = scratch<uint64_t>(c, 1, F.n);
+        uint32_t* idx = scratch<uint32_t>(c, 2, F.n);
+        uint32_t* perm = scratch<uint32_t>(c, 3, F.n);
+        LAUNCH(c, k_morton, grid_for(F.n, TB), TB, 0, c->xyz.p, F.n, c->dim, lohi, code, idx);
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, code, codes, idx, perm, F.n, 0, 63, st));
+        c->tmp.ensure(bytes, st);
+        CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, code, codes, idx, perm, F.n, 0, 63, st));
+        c->launches += 4;
+        LAUNCH(c, k_agg_from_perm, grid_for(F.n, TB), TB, 0, perm, F.n, F.agg.p);
+      } else {
+        LAUNCH(c, k_agg_consecutive, grid_for(F.n, TB), TB, 0, F.n, F.agg.p);
+      }
+      CsrRef ref{F.n, F.nnz, F.rowptr.p, F.col.p, F.val.p, F.diag.p};
+      C.nnz = galerkin(c, ref, F.agg.p, nc, C.rowptr, C.col, C.val);
+    }
     C.n = nc;
-    uint64_t* keys = scratch<uint64_t>(c, 0, F.nnz);
-    uint64_t* keys2 = scratch<uint64_t>(c, 1, F.nnz);
-    uint64_t* ukeys = scratch<uint64_t>(c, 6, F.nnz);
-    double* vals = scratch<double>(c, 2, F.nnz);
-    double* vals2 = scratch<double>(c, 3, F.nnz);
-    double* uvals = scratch<double>(c, 7, F.nnz);
-    int64_t* nruns = scratch<int64_t>(c, 9, 2);
-    // level 0 carries its Morton aggregate map; deeper levels aggregate 8 consecutive rows (agg == nullptr)
-    const int32_t* aggmap = (nlev == 2) ? F.agg.p : (const int32_t*)nullptr;
-    LAUNCH(c, k_galerkin_pairs, grid_for(F.n, TB), TB, 0, F.rowptr.p, F.col.p, F.val.p, aggmap, F.dinv.p, F.n, keys, vals);
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys, keys2, vals, vals2, F.nnz, 0, 64, st));
-    c->tmp.ensure(bytes, st);
-    CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, keys, keys2, vals, vals2, F.nnz, 0, 64, st));
-    CK(cub::DeviceReduce::ReduceByKey(nullptr, bytes, keys2, ukeys, vals2, uvals, nruns, cub::Sum(), F.nnz, st));
-    c->tmp.ensure(bytes, st);
-    CK(cub::DeviceReduce::ReduceByKey(c->tmp.p, bytes, keys2, ukeys, vals2, uvals, nruns, cub::Sum(), F.nnz, st));
-    c->launches += 8;
-    int64_t hr = 0;
-    uint64_t lastkey = 0;
-    CK(cudaMemcpyAsync(&hr, nruns, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    if (hr > 0) {
-      CK(cudaMemcpyAsync(&lastkey, ukeys + (hr - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      if (lastkey == ~0ull) hr--;  // the run of dropped (constrained) entries
+    nlev++;
+    // rows of every aggregate, ascending (deterministic restriction): stable sort of (aggregate, row)
+    {
+      uint32_t* key = scratch<uint32_t>(c, 0, F.n);
+      uint32_t* keys = scratch<uint32_t>(c, 1, F.n);
+      int32_t* row = scratch<int32_t>(c, 2, F.n);
+      F.members.ensure(F.n, st);
+      F.aggptr.ensure(nc + 1, st);
+      LAUNCH(c, k_agg_keys, grid_for(F.n, TB), TB, 0, F.agg.p, F.n, key, row);
+      CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, key, keys, row, F.members.p, F.n, 0, 32, st));
+      c->tmp.ensure(bytes, st);
+      CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, key, keys, row, F.members.p, F.n, 0, 32, st));
+      c->launches += 4;
+      LAUNCH(c, k_agg_ptr, grid_for(nc + 1, TB), TB, 0, keys, F.n, nc, F.aggptr.p);
     }
-    C.nnz = hr;
-    C.rowptr.ensure(nc + 1, st); C.col.ensure(std::max<int64_t>(hr, 1), st); C.val.ensure(std::max<int64_t>(hr, 1), st); C.dinv.ensure(nc, st);
-    LAUNCH(c, k_coarse_rowptr, grid_for(nc + 1, TB), TB, 0, ukeys, hr, nc, C.rowptr.p);
-    if (hr) {
-      LAUNCH(c, k_coarse_cols, grid_for(hr, TB), TB, 0, ukeys, hr, C.col.p);
-      CK(cudaMemcpyAsync(C.val.p, uvals, hr * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    }
-    LAUNCH(c, k_level_dinv, grid_for(nc, TB), TB, 0, C.rowptr.p, C.col.p, C.val.p, (const uint8_t*)nullptr, nc, C.dinv.p);
+    C.dinv.ensure(nc, st); C.diag.ensure(nc, st);
+    LAUNCH(c, k_level_dinv, grid_for(nc, TB), TB, 0, C.rowptr.p, C.col.p, C.val.p, (const uint8_t*)nullptr, nc, C.dinv.p, C.diag.p);
   }
   c->amg_nlev = nlev;
   for (int l = 0; l < nlev; l++) c->amg[l].omega = c->amg_omega_scale;  // l1-Jacobi: any weight <= 1 keeps the cycle SPD
@@ -441,6 +595,25 @@ void amg_setup(Ctx* c) {
   }
 }
 
+void amg_setup(Ctx* c) {
+  cudaStream_t st = c->stream;
+  const int64_t nv = c->nv;
+  if (c->amg.capacity() < MAXLEV) c->amg.reserve(MAXLEV);
+  if (c->amg.empty()) c->amg.emplace_back();
+  {
+    // ---- level 0: the leading nv x nv block of A = the P1 stiffness matrix, built without the assembled matrix: pattern
+    // from the edge list, values by the row-gather assembly restricted to the vertex rows / columns (bit-identical to the
+    // entries of the whole matrix).  Constrained vertices keep their entries but have dinv = diag = 0: their x stays 0 in
+    // every sweep, they join no aggregate and the Galerkin products drop them.
+    Ctx::AmgLevel& L = c->amg[0];
+    L.n = nv;
+    L.nnz = vertex_block_pattern(c, L.rowptr, L.col);
+    L.val.ensure(L.nnz, st); L.dinv.ensure(nv, st); L.diag.ensure(nv, st);
+    assemble_vertex_block(c, L.rowptr.p, L.col.p, L.val.p);
+    LAUNCH(c, k_level_dinv, grid_for(nv, TB), TB, 0, L.rowptr.p, L.col.p, L.val.p, c->constrained.p, nv, L.dinv.p, L.diag.p);
+  }
+  amg_build_hierarchy(c);
+}
 // work blocks of every level for k right-hand sides (grow-only; must be called before a CUDA-graph capture of amg_apply)
 void amg_prepare(Ctx* c, int k) {
   for (int l = 0; l < c->amg_nlev; l++) {
@@ -469,7 +642,7 @@ void amg_apply(Ctx* c, const double* R, double* Z, int k) {
     }
     spmm_smooth(c, L.rowptr.p, L.col.p, L.val.p, L.dinv.p, b, L.x.p, L.t.p, k, L.n, omega, 1);  // t = b - A x
     Ctx::AmgLevel& C = c->amg[l + 1];
-    LAUNCH(c, k_restrict, grid_for(C.n * k, TB), TB, 0, l == 0 ? L.members.p : (const int32_t*)nullptr, L.t.p, C.b.p, k, L.n, C.n);
+    LAUNCH(c, k_restrict, grid_for(C.n * k, TB), TB, 0, L.aggptr.p, L.members.p, L.t.p, C.b.p, k, C.n);
   }
   {  // coarsest: dense inverse
     Ctx::AmgLevel& L = c->amg[nl - 1];
@@ -483,12 +656,12 @@ void amg_apply(Ctx* c, const double* R, double* Z, int k) {
     Ctx::AmgLevel& C = c->amg[l + 1];
     const double* b = (l == 0) ? R : L.b.p;
     const double omega = L.omega;
-    LAUNCH(c, k_prolong, grid_for(L.n * k, TB), TB, 0, l == 0 ? L.agg.p : (const int32_t*)nullptr, L.dinv.p, C.x.p, L.x.p, k, L.n, alpha);
+    LAUNCH(c, k_prolong, grid_for(L.n * k, TB), TB, 0, L.agg.p, L.dinv.p, C.x.p, L.x.p, k, L.n, alpha);
     for (int s = 0; s < sweeps; s++) {
       double* out = (l == 0 && s == sweeps - 1) ? Z : L.t.p;
       spmm_smooth(c, L.rowptr.p, L.col.p, L.val.p, L.dinv.p, b, L.x.p, out, k, L.n, omega, 0);
       if (out == L.t.p) std::swap(L.x.p, L.t.p);
     }
   }
-  // the high-order rows (z = D^-1 r) are handled inside the PCG vector kernels (k_init / k_update_xr, tail_from = nv)
+  // the high-order rows (z = D^-1 r) are handled inside the PCG vector kernels (k_init / k_update_r / k_update_px, tail_from = nv)
 }

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(TB) k_assemble_rows(SpaceView s, const double*
                                                       const double* __restrict__ gm, const int64_t* __restrict__ adj_ptr,
                                                       const uint32_t* __restrict__ adj, const int64_t* __restrict__ rowptr,
                                                       const int32_t* __restrict__ col, double* __restrict__ val,
-                                                      int maxrow) {
+                                                      int maxrow, int64_t nrows, int ncl) {
   extern __shared__ double smem[];
   double* T = smem;                                 // NM*NLD*NLD
   double* rowbuf = smem + NM * NLD * NLD;           // (TB/LANES) x maxrow
@@ -110,7 +110,9 @@ __global__ void __launch_bounds__(TB) k_assemble_rows(SpaceView s, const double*
   double* acc = rowbuf + (size_t)sub * maxrow;
   // sub-warps of one warp work on different rows with different trip counts: synchronise the sub-warp only
   const unsigned full = (LANES == 32) ? 0xffffffffu : (((1u << (LANES & 31)) - 1u) << (((threadIdx.x & 31) / LANES) * LANES));
-  for (int64_t row = (int64_t)blockIdx.x * subs_per_block + sub; row < s.ndof; row += (int64_t)gridDim.x * subs_per_block) {
+  // nrows = ndof, ncl = NLD: the whole matrix.  nrows = nv, ncl = vertices per element: its leading vertex block alone
+  // (same element order, same arithmetic: bit-identical to the corresponding entries of the whole matrix)
+  for (int64_t row = (int64_t)blockIdx.x * subs_per_block + sub; row < nrows; row += (int64_t)gridDim.x * subs_per_block) {
     const int64_t rs = rowptr[row];
     const int len = (int)(rowptr[row + 1] - rs);
     const int32_t* rc = col + rs;
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(TB) k_assemble_rows(SpaceView s, const double*
       const uint32_t pay = adj[ai];
       const int64_t t = pay / NLD;
       const int a = (int)(pay - t * NLD);
-      if (lane < NLD) {
+      if (lane < ncl) {
         const double* g = gm + t * NM;
         double k = 0.0;
 #pragma unroll
@@ -148,19 +150,51 @@ __global__ void k_max_rowlen(const int64_t* __restrict__ rowptr, int64_t n, int*
   if ((threadIdx.x & 31) == 0 && len > 0) atomicMax(out, len);
 }
 
+// diag(A) straight from the element metrics: one thread per dof walks its adjacent elements in ascending order (the order
+// and the arithmetic of k_assemble_rows: bit-identical to the diagonal of the assembled matrix).  dinv = 1 / a_ii on free
+// dofs, 0 on constrained ones.
+template <int NLD, int NM>
+__global__ void __launch_bounds__(TB) k_diag_rows(const double* __restrict__ tensors, const double* __restrict__ gm,
+                                                  const int64_t* __restrict__ adj_ptr, const uint32_t* __restrict__ adj,
+                                                  const uint8_t* __restrict__ constrained, int64_t ndof, double* __restrict__ dinv) {
+  __shared__ double Td[NM * NLD];  // T[m][a][a]
+  for (int i = threadIdx.x; i < NM * NLD; i += blockDim.x) {
+    const int m = i / NLD, a = i - m * NLD;
+    Td[i] = tensors[(m * NLD + a) * NLD + a];
+  }
+  __syncthreads();
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (row >= ndof) return;
+  double d = 0.0;
+  if (!constrained[row]) {
+    for (int64_t ai = adj_ptr[row]; ai < adj_ptr[row + 1]; ai++) {
+      const uint32_t pay = adj[ai];
+      const int64_t t = pay / NLD;
+      const int a = (int)(pay - t * NLD);
+      const double* g = gm + t * NM;
+      double k = 0.0;
+#pragma unroll
+      for (int m = 0; m < NM; m++) k = fma(g[m], Td[m * NLD + a], k);
+      d += k;
+    }
+  }
+  dinv[row] = d > 0.0 ? 1.0 / d : 0.0;
+}
+
 template <int NLD, int LANES, int NM>
-void launch_rows(Ctx* c, const double* tensors_dev, int maxrow) {
+void launch_rows(Ctx* c, const double* tensors_dev, int maxrow, const int64_t* rowptr, const int32_t* col, double* val,
+                 int64_t nrows, int ncl) {
   const size_t smem = (size_t)(NM * NLD * NLD + (TB / LANES) * maxrow) * sizeof(double);
   auto kern = k_assemble_rows<NLD, LANES, NM>;
-  if (smem > 200 * 1024) FAIL(REMO_ERR_MESH, "remo_assemble: a matrix row has %d entries, too many for the row buffer", maxrow);
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int dev_max = allow_max_smem(kern, c->device);
+  if (smem > (size_t)dev_max || smem > 200 * 1024) FAIL(REMO_ERR_MESH, "remo_assemble: a matrix row has %d entries, too many for the row buffer", maxrow);
   int per_sm = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TB, smem));
   if (per_sm < 1) per_sm = 1;
-  const int64_t want = (c->ndof + (TB / LANES) - 1) / (TB / LANES);
+  const int64_t want = (nrows + (TB / LANES) - 1) / (TB / LANES);
   const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)c->num_sms * per_sm);
   SpaceView sview = make_view(c);
-  kern<<<grid, TB, smem, c->stream>>>(sview, tensors_dev, c->gm.p, c->adj_ptr.p, c->adj.p, c->rowptr.p, c->col.p, c->val.p, maxrow);
+  kern<<<grid, TB, smem, c->stream>>>(sview, tensors_dev, c->gm.p, c->adj_ptr.p, c->adj.p, rowptr, col, val, maxrow, nrows, ncl);
   c->launches++;
   CK(cudaGetLastError());
 }
@@ -193,10 +227,7 @@ const double* tensors_for(Ctx* c) {
   return d;
 }
 
-}  // namespace
-
-// geometry + row-gather kernels (also timed alone by remo_kernel_time which=1)
-void assemble_kernels_only(Ctx* c) {
+void geometry(Ctx* c) {
   cudaStream_t st = c->stream;
   const int nm = (c->dim == 3) ? 10 : 18;
   c->gm.ensure(c->nt * nm, st);
@@ -207,24 +238,76 @@ void assemble_kernels_only(Ctx* c) {
     LAUNCH(c, k_geom_tet, grid_for(c->nt, TB), TB, 0, c->sv.p, c->xyz.p, c->mat.p, c->sigma.p, (int)c->sigma.n, c->gm.p, c->nt, bad.p);
   else
     LAUNCH(c, k_geom_tri, grid_for(c->nt, TB), TB, 0, c->sv.p, c->xyz.p, c->mat.p, c->sigma.p, (int)c->sigma.n, c->gm.p, c->nt, bad.p);
-  LAUNCH(c, k_max_rowlen, grid_for(c->ndof, TB), TB, 0, c->rowptr.p, c->ndof, bad.p + 1);
-  int hb[2] = {0, 0};
-  CK(cudaMemcpyAsync(hb, bad.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  int hb = 0;
+  CK(cudaMemcpyAsync(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   bad.release(st);
-  if (hb[0] == 1) FAIL(REMO_ERR_ARG, "remo_assemble: a material index is outside the sigma list (nmat=%d)", (int)c->sigma.n);
-  if (hb[0] == 2) FAIL(REMO_ERR_MESH, "remo_assemble: degenerate (zero volume) element");
-  const int maxrow = (hb[1] + 7) & ~7;
+  if (hb == 1) FAIL(REMO_ERR_ARG, "remo_assemble: a material index is outside the sigma list (nmat=%d)", (int)c->sigma.n);
+  if (hb == 2) FAIL(REMO_ERR_MESH, "remo_assemble: degenerate (zero volume) element");
+}
+
+// row-gather assembly into a CSR pattern: the whole matrix (nrows = ndof, ncl = nld) or its vertex block (nrows = nv, ncl = dim + 1)
+void assemble_rows(Ctx* c, const int64_t* rowptr, const int32_t* col, double* val, int64_t nrows, int ncl) {
+  cudaStream_t st = c->stream;
+  int* mx = scratch<int>(c, 8, 4);
+  CK(cudaMemsetAsync(mx, 0, sizeof(int), st));
+  LAUNCH(c, k_max_rowlen, grid_for(nrows, TB), TB, 0, rowptr, nrows, mx);
+  int hm = 0;
+  CK(cudaMemcpyAsync(&hm, mx, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const int maxrow = (hm + 7) & ~7;
   const double* T = tensors_for(c);
   if (c->dim == 3) {
-    if (c->order == 1) launch_rows<4, 4, 10>(c, T, maxrow);
-    if (c->order == 2) launch_rows<10, 16, 10>(c, T, maxrow);
-    if (c->order == 3) launch_rows<20, 32, 10>(c, T, maxrow);
+    if (c->order == 1) launch_rows<4, 4, 10>(c, T, maxrow, rowptr, col, val, nrows, ncl);
+    if (c->order == 2) launch_rows<10, 16, 10>(c, T, maxrow, rowptr, col, val, nrows, ncl);
+    if (c->order == 3) launch_rows<20, 32, 10>(c, T, maxrow, rowptr, col, val, nrows, ncl);
   } else {
-    if (c->order == 1) launch_rows<3, 4, 18>(c, T, maxrow);
-    if (c->order == 2) launch_rows<6, 8, 18>(c, T, maxrow);
-    if (c->order == 3) launch_rows<10, 16, 18>(c, T, maxrow);
+    if (c->order == 1) launch_rows<3, 4, 18>(c, T, maxrow, rowptr, col, val, nrows, ncl);
+    if (c->order == 2) launch_rows<6, 8, 18>(c, T, maxrow, rowptr, col, val, nrows, ncl);
+    if (c->order == 3) launch_rows<10, 16, 18>(c, T, maxrow, rowptr, col, val, nrows, ncl);
   }
+}
+
+}  // namespace
+
+// geometry + row-gather kernels of the whole matrix (also timed alone by remo_kernel_time which=1)
+void assemble_kernels_only(Ctx* c) {
+  pattern_build(c);
+  geometry(c);
+  assemble_rows(c, c->rowptr.p, c->col.p, c->val.p, c->ndof, c->nld);
+  c->have_values = true;
+}
+
+// The CSR values exist only when somebody needs them (remo_matrix_get, the SELL / CSR SpMM kernels): the element-wise PCG
+// product, diag(A) and the vertex block of the V-cycle all come straight from the element metrics gm.
+void ensure_values(Ctx* c) {
+  if (!c->have_matrix) FAIL(REMO_ERR_STATE, "matrix not assembled (call remo_assemble first)");
+  if (c->have_values) return;
+  pattern_build(c);
+  assemble_rows(c, c->rowptr.p, c->col.p, c->val.p, c->ndof, c->nld);
+  c->have_values = true;
+}
+
+// dinv = 1 / diag(A) on free dofs, 0 on constrained ones, from the element metrics
+void diag_from_elements(Ctx* c, double* dinv) {
+  const double* T = tensors_for(c);
+  const unsigned g = grid_for(c->ndof, TB);
+#define DIAG(NLD_, NM_) LAUNCH(c, (k_diag_rows<NLD_, NM_>), g, TB, 0, T, c->gm.p, c->adj_ptr.p, c->adj.p, c->constrained.p, c->ndof, dinv)
+  if (c->dim == 3) {
+    if (c->order == 1) DIAG(4, 10);
+    if (c->order == 2) DIAG(10, 10);
+    if (c->order == 3) DIAG(20, 10);
+  } else {
+    if (c->order == 1) DIAG(3, 18);
+    if (c->order == 2) DIAG(6, 18);
+    if (c->order == 3) DIAG(10, 18);
+  }
+#undef DIAG
+}
+
+// values of the vertex block (P1 stiffness matrix in the hierarchical basis) into the pattern (rowptr, col) of vertex_block_pattern
+void assemble_vertex_block(Ctx* c, const int64_t* rowptr, const int32_t* col, double* val) {
+  assemble_rows(c, rowptr, col, val, c->nv, c->dim + 1);
 }
 
 void assemble(Ctx* c, int nmat, const double* sigma) {
@@ -233,8 +316,11 @@ void assemble(Ctx* c, int nmat, const double* sigma) {
   StageTimer timer(c, ST_ASM);
   c->sigma.ensure(nmat, c->stream);
   CK(cudaMemcpyAsync(c->sigma.p, sigma, nmat * sizeof(double), cudaMemcpyDefault, c->stream));
-  assemble_kernels_only(c);
+  c->have_matrix = false;
+  c->have_values = false;
+  geometry(c);
   c->have_matrix = true;
+  if (!c->lazy_matrix) ensure_values(c);
   c->have_sell = false;
   c->have_ebe = false;
   c->pkind = -1;

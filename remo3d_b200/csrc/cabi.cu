@@ -99,7 +99,7 @@ int remo_ctx_destroy(void* vctx) {
   c->face_keys.release(s); c->elem_faces.release(s); c->constrained.release(s); c->adj_ptr.release(s); c->adj.release(s);
   c->rowptr.release(s); c->col.release(s); c->val.release(s); c->gm.release(s); c->sigma.release(s); c->rvert.release(s);
   c->dinv.release(s); amg_release(c);
-  c->F.release(s); c->X.release(s); c->R.release(s); c->Z.release(s); c->P.release(s); c->Q.release(s);
+  c->F.release(s); c->X.release(s); c->R.release(s); c->B0.release(s); c->Zv.release(s); c->P.release(s); c->Q.release(s);
   c->partial.release(s); c->scal.release(s); c->iters_d.release(s); c->tmp.release(s);
   c->sell_ptr.release(s); c->sell_col.release(s); c->sell_val.release(s); c->sell_row.release(s); c->sell_part.release(s);
   c->sell_wpart.release(s); c->bbox.release(s);
@@ -139,6 +139,7 @@ int remo_mesh_set(void* vctx, int dim, int64_t nv, const double* xyz, int64_t nt
     if (naxis < 0 || (naxis > 0 && !axis_vertices)) FAIL(REMO_ERR_ARG, "remo_mesh_set: axis array missing");
     StageTimer timer(c, ST_MESH);
     cudaStream_t st = c->stream;
+    c->have_pattern = c->have_values = false;
     c->have_mesh = c->have_bbox = c->have_space = c->have_matrix = c->have_sell = c->have_ebe = c->have_rhs = c->have_solution = false;
     c->pkind = -1;
     c->dim = dim; c->nv = nv; c->nt = nt; c->nb = nb; c->naxis = naxis;
@@ -203,10 +204,48 @@ int remo_matrix_get(void* vctx, int64_t* rowptr, int32_t* col, double* val) {
   return guarded(vctx, [&](Ctx* c) {
     if (!c->have_space) FAIL(REMO_ERR_STATE, "remo_matrix_get: no space");
     if (val && !c->have_matrix) FAIL(REMO_ERR_STATE, "remo_matrix_get: matrix not assembled");
+    pattern_build(c);            // lazy: the PCG path of order-2 tets never builds the CSR matrix
+    if (val) ensure_values(c);
     cudaStream_t st = c->stream;
     if (rowptr) CK(cudaMemcpyAsync(rowptr, c->rowptr.p, (c->ndof + 1) * sizeof(int64_t), cudaMemcpyDefault, st));
     if (col) CK(cudaMemcpyAsync(col, c->col.p, c->nnz * sizeof(int32_t), cudaMemcpyDefault, st));
     if (val) CK(cudaMemcpyAsync(val, c->val.p, c->nnz * sizeof(double), cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
+    return REMO_OK;
+  });
+}
+
+int remo_matrix_nnz(void* vctx, int64_t* nnz) {
+  return guarded(vctx, [&](Ctx* c) {
+    if (!nnz) FAIL(REMO_ERR_ARG, "remo_matrix_nnz: NULL argument");
+    pattern_build(c);
+    *nnz = c->nnz;
+    return REMO_OK;
+  });
+}
+
+int remo_precond_get(void* vctx, double* dinv, int64_t* vv_rowptr, int32_t* vv_col, double* vv_val, int* nlevels, int64_t* level_rows,
+                     int64_t* level_nnz) {
+  return guarded(vctx, [&](Ctx* c) {
+    if (c->pkind < 0) FAIL(REMO_ERR_STATE, "remo_precond_get: no preconditioner (call remo_precond_setup first)");
+    cudaStream_t st = c->stream;
+    if (dinv) CK(cudaMemcpyAsync(dinv, c->dinv.p, c->ndof * sizeof(double), cudaMemcpyDefault, st));
+    const bool mg = c->pkind == REMO_PRECOND_MULTIGRID;
+    if ((vv_rowptr || vv_col || vv_val) && !mg) FAIL(REMO_ERR_STATE, "remo_precond_get: the vertex block exists only for the multigrid preconditioner");
+    if (mg) {
+      const Ctx::AmgLevel& L = c->amg[0];
+      if (vv_rowptr) CK(cudaMemcpyAsync(vv_rowptr, L.rowptr.p, (L.n + 1) * sizeof(int64_t), cudaMemcpyDefault, st));
+      if (vv_col) CK(cudaMemcpyAsync(vv_col, L.col.p, L.nnz * sizeof(int32_t), cudaMemcpyDefault, st));
+      if (vv_val) CK(cudaMemcpyAsync(vv_val, L.val.p, L.nnz * sizeof(double), cudaMemcpyDefault, st));
+    }
+    if (nlevels) {
+      const int cap = *nlevels;
+      *nlevels = mg ? c->amg_nlev : 0;
+      for (int l = 0; mg && l < c->amg_nlev && l < cap; l++) {
+        if (level_rows) level_rows[l] = c->amg[l].n;
+        if (level_nnz) level_nnz[l] = c->amg[l].nnz;
+      }
+    }
     CK(cudaStreamSynchronize(st));
     return REMO_OK;
   });
@@ -329,7 +368,7 @@ int remo_spmm_apply(void* vctx, int nrhs, const double* p, double* q, double* pq
     if (nrhs < 1 || nrhs > REMO_MAX_RHS || !p || !q || !pq) FAIL(REMO_ERR_ARG, "remo_spmm_apply: bad arguments");
     cudaStream_t st = c->stream;
     if (c->pkind < 0) precond_setup(c, REMO_PRECOND_LOCAL);
-    const int ks = solver_stride(nrhs);
+    const int ks = solver_stride(c, nrhs);
     alloc_solver_state(c, ks);
     c->nrhs_user = nrhs;
     c->have_rhs = c->have_solution = false;
@@ -366,6 +405,10 @@ int remo_set_option(void* vctx, const char* name, double value) {
     else if (n == "amg_sweeps") c->amg_sweeps = std::max(1, (int)value);
     else if (n == "spmm_ebe") { c->ebe_on = value != 0.0 ? 1 : 0; c->have_ebe = false; c->pkind = -1; }
     else if (n == "amg_omega_scale") { c->amg_omega_scale = value; c->pkind = -1; }
+    else if (n == "amg_agg") { c->amg_agg = value != 0.0 ? 1 : 0; c->pkind = -1; }
+    else if (n == "amg_passes") { c->amg_passes = std::min(8, std::max(1, (int)value)); c->pkind = -1; }
+    else if (n == "amg_rounds") { c->amg_rounds = std::min(32, std::max(1, (int)value)); c->pkind = -1; }
+    else if (n == "lazy_matrix") c->lazy_matrix = value != 0.0;
     else FAIL(REMO_ERR_ARG, "remo_set_option: unknown option '%s'", name);
     return REMO_OK;
   });

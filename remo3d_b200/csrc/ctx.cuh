@@ -4,7 +4,10 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <mutex>
+#include <set>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/remo3d_b200.h"
@@ -98,7 +101,10 @@ struct Ctx {
   DBuf<int64_t> rowptr;       // ndof+1
   DBuf<int32_t> col;          // nnz, ascending per row
   DBuf<double> val;           // nnz
-  bool have_space = false, have_matrix = false;
+  // have_space: topology, dofs, Dirichlet mask, adjacency.  have_pattern: rowptr / col.  have_matrix: the element metrics gm
+  // of the current sigma (all the element-wise PCG path needs).  have_values: val filled for that gm.
+  bool have_space = false, have_matrix = false, have_pattern = false, have_values = false;
+  bool lazy_matrix = true;  // build the CSR pattern / values only on demand (remo_set_option("lazy_matrix", 0): eagerly)
   // sliced-ELLPACK copy of the matrix for the multi-RHS PCG SpMM (sell.cu): slices of 8 rows, chunks of 4 entries
   DBuf<int64_t> sell_ptr;   // nslices+1: first chunk of every slice
   DBuf<int32_t> sell_col;   // chunks x 8 rows x 4
@@ -139,13 +145,25 @@ struct Ctx {
     int64_t n = 0, nnz = 0;
     DBuf<int64_t> rowptr;
     DBuf<int32_t> col;
-    DBuf<double> val, dinv;
-    DBuf<int32_t> agg;        // fine row -> aggregate (coarse row) of the next level
-    DBuf<int32_t> members;    // rows sorted by aggregate (8 per aggregate, -1 padded): deterministic restriction
+    DBuf<double> val, dinv;   // dinv: l1-Jacobi weights 1 / sum_j |a_ij| (0 = row outside the coarse space)
+    DBuf<double> diag;        // a_ii (0 on rows outside the coarse space): coupling strengths of the pairwise aggregation
+    DBuf<int32_t> agg;        // fine row -> aggregate (coarse row) of the next level, -1 = none
+    DBuf<int32_t> members;    // rows sorted by aggregate, ascending inside one: deterministic restriction
+    DBuf<int32_t> aggptr;     // nc + 1: first entry of every aggregate in members
     double omega = 1.0;       // weight of the l1-Jacobi sweeps
     DBuf<double> b, x, t;     // n x nrhs work blocks (level 0 uses R / Z of the PCG directly for b / x)
   };
   std::vector<AmgLevel> amg;
+  struct AmgTmp {  // Galerkin products between the passes of one level's pairwise aggregation
+    int64_t n = 0, nnz = 0;
+    DBuf<int64_t> rowptr;
+    DBuf<int32_t> col;
+    DBuf<double> val, diag;
+  } amg_tmp[2];
+  DBuf<int32_t> amg_w[5];    // match, pick, flag, scan, id of the current pass
+  int amg_agg = 1;           // 1 = strength-based pairwise aggregation, 0 = Morton-rank aggregates of 8 (round 1)
+  int amg_passes = 3;        // pairwise passes per level: aggregates of at most 2^passes rows
+  int amg_rounds = 4;        // handshake rounds per pass
   double amg_alpha = 1.5, amg_omega_scale = 1.0;  // coarse-correction scaling, weight of the l1-Jacobi sweeps (<= 1)
   int amg_sweeps = 1;                              // pre = post smoothing sweeps
   int amg_gamma = 1;                               // cycle index: 1 = V, 2 = W
@@ -157,7 +175,9 @@ struct Ctx {
   int nrhs = 0;       // internal column count = row stride of the vector blocks (user count rounded up to even)
   int nrhs_user = 0;  // right-hand sides the caller asked for
   int pstride = 0;    // row stride of the P block alone: = nrhs, or the next power of two when the SELL SpMM gathers it
-  DBuf<double> F, X, R, Z, P, Q;
+  DBuf<double> F, X, R, P, Q;
+  int kz = 0;            // row stride (even) of the V-cycle's blocks B0 / Zv
+  DBuf<double> B0, Zv;   // nv x kz: residual of the vertex rows (right-hand side of the V-cycle) and its result
   DBuf<double> partial;  // per-block partial dot products
   DBuf<double> scal;     // device scalars, see solver.cu
   DBuf<int> iters_d;
@@ -191,6 +211,24 @@ static inline T* scratch(Ctx* c, int slot, size_t count) {
     CK(cudaGetLastError());                                            \
   } while (0)
 
+// Dynamic shared memory above 48 KB needs cudaFuncAttributeMaxDynamicSharedMemorySize, which is per-function,
+// process-wide state: several contexts (host threads) solve different meshes on one GPU, so the limit is raised ONCE per
+// (kernel, device) to the device's opt-in maximum and never lowered; callers only check their own size against it.
+template <typename K>
+static inline int allow_max_smem(K kern, int device) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev_max = 0;
+  CK(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  std::lock_guard<std::mutex> g(mu);
+  const auto key = std::make_pair((const void*)kern, device);
+  if (!done.count(key)) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_max));
+    done.insert(key);
+  }
+  return dev_max;
+}
+
 static inline unsigned grid_for(int64_t n, int block, int64_t cap = (1 << 30)) {
   int64_t g = (n + block - 1) / block;
   if (g < 1) g = 1;
@@ -210,10 +248,15 @@ struct StageTimer {
 
 // symbolic.cu
 void space_build(Ctx* c, int order);
+void pattern_build(Ctx* c);
+int64_t vertex_block_pattern(Ctx* c, DBuf<int64_t>& rowptr, DBuf<int32_t>& col);
 void topology_get(Ctx* c, int32_t* edges, int32_t* faces, int32_t* elem_edges, int32_t* elem_faces);
 // assemble.cu
 void assemble(Ctx* c, int nmat, const double* sigma);
 void assemble_kernels_only(Ctx* c);
+void ensure_values(Ctx* c);
+void diag_from_elements(Ctx* c, double* dinv);
+void assemble_vertex_block(Ctx* c, const int64_t* rowptr, const int32_t* col, double* val);
 // solver.cu
 void precond_setup(Ctx* c, int kind);
 void rhs_point_sources(Ctx* c, int nrhs, const int64_t* src_ptr, const double* src_z, const double* src_fac);
@@ -227,7 +270,7 @@ void alloc_solver_state(Ctx* c, int nrhs);
 int spmm_variant();
 void spmm_prepare(Ctx* c);
 int spmm_kind(Ctx* c);
-int solver_stride(int nrhs);       // row stride of the PCG vector blocks for nrhs right-hand sides
+int solver_stride(const Ctx* c, int nrhs);  // row stride of the PCG vector blocks for nrhs right-hand sides
 int spmm_blocks(Ctx* c, int ks);   // CTAs (= partial-dot slots) of the SpMM launch for stride ks
 // sell.cu
 const double* mesh_bbox(Ctx* c);
@@ -238,11 +281,13 @@ void launch_spmm_sell(Ctx* c, const double* P, double* Q, int ks, int pstride);
 // ebe.cu
 bool ebe_eligible(const Ctx* c);
 bool ebe_usable(const Ctx* c, int nr);
+int ebe_max_rhs();
 void ebe_build(Ctx* c);
 int ebe_grid(const Ctx* c, int nr);
 void launch_spmm_ebe(Ctx* c, const double* P, int pstride, double* Q, int ks, int nr);
 // amg.cu
 void amg_setup(Ctx* c);
+void amg_build_hierarchy(Ctx* c);
 void amg_apply(Ctx* c, const double* R, double* Z, int nrhs);
 void amg_prepare(Ctx* c, int nrhs);
 void amg_release(Ctx* c);

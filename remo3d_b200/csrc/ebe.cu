@@ -61,17 +61,37 @@ __global__ void k_tet_morton(const int32_t* __restrict__ sv, const double* __res
 }
 
 // One CTA per batch.  FILL = false: count the distinct dofs; true: write the batch tables at the offsets uoff[].
+//
+// Conflict-aware layout (color != 0, pieces of at most 8 entries).  The product kernel makes two random 8-byte
+// shared-memory accesses per (tet, slot, right-hand side): it GATHERS the staged row of the slot's dof (address ~ row)
+// and SCATTERS the element's result to entry i of that dof in the jagged-diagonal scratch (address jd[i] + row).  The 16
+// lanes of a half-warp executing one slot form a GROUP; a group's request costs one wavefront per distinct address in its
+// busiest 8-byte bank pair, and with rows / entry orders taken as they come that is 2.4 (gathers) and 3.0 (scatters)
+// wavefronts instead of 1 (tools/ebe_layout_sim.py; ncu: 40 M of the 120 M wavefronts of a product were conflicts).
+// Both layouts have slack: a piece may take ANY row of its entry-count class, and the entries of a piece may take its
+// indices 0..n-1 in ANY order.  Warp 0 deals them greedily, pieces with the most groups first: the row whose bank pair
+// (row mod 16) is least used in the piece's groups, then for every entry the free index whose scratch bank pair is least
+// used in the entry's group.  Model: 1.2 / 2.3 wavefronts per request.  Fixed visiting order -> the tables, and with
+// them the summation order of the product, are reproducible.
 template <bool FILL>
 __global__ void __launch_bounds__(TPB) k_ebe_batch(SpaceView s, const int32_t* __restrict__ tperm,
-                                                   int split, const uint8_t* __restrict__ constrained, int64_t* __restrict__ ucount,
+                                                   int split, int color, const uint8_t* __restrict__ constrained, int64_t* __restrict__ ucount,
                                                    int* __restrict__ umax, const int64_t* __restrict__ uoff,
                                                    int32_t* __restrict__ udof, uint16_t* __restrict__ lidx,
                                                    uint16_t* __restrict__ lpos, uint16_t* __restrict__ ucnt, uint16_t* __restrict__ jdp) {
   using Sort = cub::BlockRadixSort<uint32_t, TPB, NLD, uint16_t>;
   using Scan = cub::BlockScan<int, TPB>;
+  constexpr int NGRP = (TPB / 16) * NLD;  // gather / scatter groups of a batch: (half-warp, slot)
+  struct Greedy {
+    uint8_t gocc[NGRP * 16];   // rows already dealt per (group, bank pair)
+    uint8_t socc[NGRP * 16];   // scratch entries already dealt per (group, bank pair)
+    uint8_t sidx[TPB * NLD];   // sorted entry -> its index inside its piece
+    uint16_t nxt[9 * 16];      // next free row per (entry-count class, bank pair)
+  };
   __shared__ union Tmp {
     typename Sort::TempStorage sort;
     typename Scan::TempStorage scan;
+    Greedy g;
   } tmp;
   __shared__ uint32_t skey[TPB * NLD];
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -127,15 +147,20 @@ __global__ void __launch_bounds__(TPB) k_ebe_batch(SpaceView s, const int32_t* _
   // smaller index i.  One thread per dof then walks i = 0 .. count-1: neighbouring lanes read neighbouring words (no
   // bank conflicts) and the lanes of a warp have (almost) the same trip count -- a vertex has 20-40 entries in a
   // batch, an edge ~3, and in dof order they would share warps.
-  __shared__ uint16_t spos[TPB * NLD + 1];  // first sorted position of every dof (by its rank in dof order)
-  __shared__ uint16_t snew[TPB * NLD];      // rank in dof order -> rank by entry count
+  __shared__ uint16_t spos[TPB * NLD + 1];  // first sorted position of every piece (by its rank in dof order)
+  __shared__ uint16_t srow[TPB * NLD];      // rank in dof order -> row (rank by entry count, permuted inside its class)
+  __shared__ uint16_t sord[TPB * NLD];      // rank by entry count -> rank in dof order
+  __shared__ uint16_t sval[TPB * NLD];      // sorted position -> slot * 256 + tet
   __shared__ uint16_t sjd[EBE_JD];
+  const bool colored = color != 0 && split > 0 && split <= 8;
   const int nvalid = (int)((s.nt - (int64_t)b * TPB < TPB ? s.nt - (int64_t)b * TPB : TPB) * NLD);
   {
     int cnt = 0;
 #pragma unroll
-    for (int k = 0; k < NLD; k++)
+    for (int k = 0; k < NLD; k++) {
       if (head[k]) spos[base + cnt++] = (uint16_t)(tid * NLD + k);
+      sval[tid * NLD + k] = val[k];
+    }
     if (tid == 0) spos[total] = (uint16_t)nvalid;  // padding tets sort behind every real entry
   }
   __syncthreads();
@@ -144,17 +169,32 @@ __global__ void __launch_bounds__(TPB) k_ebe_batch(SpaceView s, const int32_t* _
 #pragma unroll
   for (int k = 0; k < NLD; k++) {
     const int rho = tid * NLD + k;
-    ckey[k] = rho < total ? 0xffffu - (uint32_t)(spos[rho + 1] - spos[rho]) : SENT;
     cval[k] = (uint16_t)rho;
+    if (rho >= total) { ckey[k] = SENT; continue; }
+    const int p0 = spos[rho], n = spos[rho + 1] - p0;
+    if (!colored) { ckey[k] = 0xffffu - (uint32_t)n; continue; }
+    // entries descending, then pieces that touch the most groups first (they are the hardest to place)
+    int ngr = 0;
+    uint32_t seen[8];
+    for (int e = 0; e < n; e++) {
+      const uint32_t v = sval[p0 + e];
+      const uint32_t g = ((v & (TPB - 1)) >> 4) * NLD + (v >> 8);
+      bool dup = false;
+      for (int f = 0; f < ngr; f++) dup |= seen[f] == g;
+      if (!dup) seen[ngr++] = g;
+    }
+    ckey[k] = ((uint32_t)(8 - n) << 4) | (uint32_t)(8 - ngr);
   }
   Sort(tmp.sort).Sort(ckey, cval);
   uint32_t* scount = skey;  // entry counts by new rank (descending); the sorted dof keys are no longer needed
+  __syncthreads();          // every thread has read skey (head flags) and the sort is done with its temp storage
 #pragma unroll
   for (int k = 0; k < NLD; k++) {
     const int j = tid * NLD + k;
     if (j < total) {
-      snew[cval[k]] = (uint16_t)j;
-      scount[j] = 0xffffu - ckey[k];
+      sord[j] = cval[k];
+      srow[cval[k]] = (uint16_t)j;
+      scount[j] = colored ? 8u - (ckey[k] >> 4) : 0xffffu - ckey[k];
     }
   }
   __syncthreads();
@@ -180,15 +220,93 @@ __global__ void __launch_bounds__(TPB) k_ebe_batch(SpaceView s, const int32_t* _
       jdp[(int64_t)b * EBE_JD + i] = (uint16_t)jd[k];
     }
   }
-  __syncthreads();
+  __syncthreads();  // sjd complete; the scan is done with its temp storage
+  if (colored) {
+    Greedy& G = tmp.g;
+    for (int i = tid; i < NGRP * 16; i += TPB) { G.gocc[i] = 0; G.socc[i] = 0; }
+    if (tid < 9 * 16) {
+      // class c (pieces of c entries) owns the rows [lo, hi): lo = pieces with more than c entries.  First row of the
+      // class in bank pair r: lo + ((r - lo) mod 16)
+      const int c = tid >> 4, r = tid & 15;
+      int lo = 0;
+      if (c >= 1) {
+        int l = 0, h = total;
+        while (l < h) {
+          const int mid = (l + h) >> 1;
+          if (scount[mid] > (uint32_t)c) l = mid + 1; else h = mid;
+        }
+        lo = l;
+      }
+      G.nxt[tid] = (uint16_t)(lo + ((r - lo) & 15));
+    }
+    __syncthreads();
+    if (tid < 32) {
+      const int lane = tid;
+      for (int j = 0; j < total; j++) {
+        const int rho = sord[j], n = (int)scount[j];
+        const int p0 = spos[rho];
+        // class range end: first rank with a smaller count = pieces with at least n entries
+        // (ranks are count-descending, so it is the first j' with scount[j'] < n; found once per class below)
+        // ---- row: least used bank pair of the piece's groups, among the bank pairs that still have a row in the class
+        uint32_t cost = 0xffffu;
+        if (lane < 16) {
+          const int row = G.nxt[n * 16 + lane];
+          // the row is free iff it is still inside the class: rows of the class are [lo, hi) and hi = lo + size; a row
+          // index >= total or with another count is outside
+          if (row < total && (int)scount[row] == n) {
+            cost = 0;
+            for (int e = 0; e < n; e++) {
+              const uint32_t v = sval[p0 + e];
+              cost += G.gocc[(((v & (TPB - 1)) >> 4) * NLD + (v >> 8)) * 16 + lane];
+            }
+          }
+        }
+        uint32_t best = (cost << 8) | (uint32_t)(lane & 15);
+#pragma unroll
+        for (int o = 8; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+        best = __shfl_sync(0xffffffffu, best, 0);  // lanes 16..31 computed on dummies: take the half-warp's result
+        const int r = (int)(best & 15u);
+        const int row = G.nxt[n * 16 + r];
+        __syncwarp();
+        if (lane == 0) {
+          G.nxt[n * 16 + r] = (uint16_t)(row + 16);
+          srow[rho] = (uint16_t)row;
+          for (int e = 0; e < n; e++) {
+            const uint32_t v = sval[p0 + e];
+            G.gocc[(((v & (TPB - 1)) >> 4) * NLD + (v >> 8)) * 16 + r]++;
+          }
+        }
+        // ---- entry order: every entry takes the free index whose scratch bank pair is least used in its group
+        uint32_t avail = (1u << n) - 1u;
+        for (int e = 0; e < n; e++) {
+          const uint32_t v = sval[p0 + e];
+          const int g = (int)(((v & (TPB - 1)) >> 4) * NLD + (v >> 8));
+          uint32_t c2 = 0xffffu;
+          if (lane < n && ((avail >> lane) & 1u)) c2 = G.socc[g * 16 + ((sjd[lane] + row) & 15)];
+          uint32_t b2 = (c2 << 8) | (uint32_t)(lane & 7);
+#pragma unroll
+          for (int o = 4; o; o >>= 1) b2 = min(b2, __shfl_xor_sync(0xffffffffu, b2, o));
+          b2 = __shfl_sync(0xffffffffu, b2, 0);
+          const int i = (int)(b2 & 7u);
+          avail &= ~(1u << i);
+          if (lane == 0) {
+            G.sidx[p0 + e] = (uint8_t)i;
+            G.socc[g * 16 + ((sjd[i] + row) & 15)]++;
+          }
+          __syncwarp();
+        }
+      }
+    }
+    __syncthreads();
+  }
   int cnt = 0;
 #pragma unroll
   for (int k = 0; k < NLD; k++) {
     const int pos = tid * NLD + k;
     if (head[k]) cnt++;
-    const int rho = base + cnt - 1;  // rank (dof order) of the dof this entry belongs to
+    const int rho = base + cnt - 1;  // rank (dof order) of the piece this entry belongs to
     const bool real = key[k] != SENT;
-    const int nr = real ? snew[rho] : 0;
+    const int nr = real ? srow[rho] : 0;
     if (head[k]) {
       udof[u0 + nr] = (int32_t)(key[k] | (constrained[key[k]] ? 0x80000000u : 0u));
       ucnt[u0 + nr] = (uint16_t)(spos[rho + 1] - spos[rho]);
@@ -196,7 +314,8 @@ __global__ void __launch_bounds__(TPB) k_ebe_batch(SpaceView s, const int32_t* _
     lidx[bo + val[k]] = (uint16_t)nr;
     // a dof appears at most once per tet: at most 256 entries, so i < EBE_JD.  Padding tets keep a slot behind the
     // nvalid real entries
-    lpos[bo + val[k]] = (uint16_t)(real ? sjd[pos - spos[rho]] + nr : pos);
+    const int i = real ? (colored ? (int)tmp.g.sidx[pos] : pos - spos[rho]) : 0;
+    lpos[bo + val[k]] = (uint16_t)(real ? sjd[i] + nr : pos);
   }
 }
 
@@ -422,6 +541,8 @@ bool ebe_eligible(const Ctx* c) {
   return c->dim == 3 && c->order == 2 && c->ndof < 0x7fffffff;
 }
 
+int ebe_max_rhs() { return EBE_USE_RHS; }
+
 bool ebe_usable(const Ctx* c, int nr) { return c->have_ebe && nr >= 1 && nr <= EBE_USE_RHS && c->ebe_occ[nr] > 0; }
 
 int ebe_grid(const Ctx* c, int nr) { return (int)std::min<int64_t>(c->ebe_nb, (int64_t)c->num_sms * c->ebe_occ[nr]); }
@@ -447,7 +568,8 @@ void ebe_build(Ctx* c) {
   int* umax_d = scratch<int>(c, 6, 1);
   CK(cudaMemsetAsync(umax_d, 0, sizeof(int), st));
   SpaceView sview = make_view(c);
-  LAUNCH(c, k_ebe_batch<false>, (unsigned)nb, TPB, 0, sview, tperm, split, c->constrained.p, ucount, umax_d, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  static const int color = [] { const char* e = getenv("REMO_EBE_COLOR"); return e ? atoi(e) : 1; }();
+  LAUNCH(c, k_ebe_batch<false>, (unsigned)nb, TPB, 0, sview, tperm, split, color, c->constrained.p, ucount, umax_d, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
   LAUNCH(c, k_ebe_offsets_in, grid_for(nb + 1, TPB), TPB, 0, ucount, nb, uin);
   c->ebe_uoff.ensure(nb + 1, st);
   CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, uin, c->ebe_uoff.p, nb + 1, st));
@@ -467,7 +589,7 @@ void ebe_build(Ctx* c) {
   c->ebe_lidx.ensure((size_t)nb * TPB * NLD, st);
   c->ebe_lpos.ensure((size_t)nb * TPB * NLD, st);
   c->ebe_gm.ensure((size_t)nb * TPB * NLD, st);
-  LAUNCH(c, k_ebe_batch<true>, (unsigned)nb, TPB, 0, sview, tperm, split, c->constrained.p, nullptr, nullptr, c->ebe_uoff.p, c->ebe_udof.p,
+  LAUNCH(c, k_ebe_batch<true>, (unsigned)nb, TPB, 0, sview, tperm, split, color, c->constrained.p, nullptr, nullptr, c->ebe_uoff.p, c->ebe_udof.p,
          c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_ucnt.p, c->ebe_jd.p);
   LAUNCH(c, k_ebe_gm, grid_for(nb * TPB, TPB), TPB, 0, c->gm.p, tperm, nt, nb, c->ebe_gm.p);
   c->ebe_nb = nb;

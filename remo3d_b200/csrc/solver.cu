@@ -244,11 +244,12 @@ __device__ __forceinline__ void flat_partials(double a0, double a1, double b0, d
   }
 }
 
-// X = 0, R = masked F, Z = dinv R and P = Z on rows >= tail_from; partials: [0] = r.r (= b.b), [1] = r.z over those rows
+// X = 0, R = masked F; rows >= tail_from: P = z = dinv r; rows < tail_from (preconditioned by the V-cycle): r goes to the
+// V-cycle's right-hand-side block B0 (row stride kz).  partials: [0] = r.r (= b.b), [1] = r.z over the rows >= tail_from
 template <int W>
 __global__ void __launch_bounds__(TB) k_init(const double* __restrict__ F, const uint8_t* __restrict__ constrained,
                                              const double* __restrict__ dinv, double* __restrict__ X, double* __restrict__ R,
-                                             double* __restrict__ Z, double* __restrict__ P, int ks, int kps, int64_t n,
+                                             double* __restrict__ B0, double* __restrict__ P, int ks, int kps, int kz, int64_t n,
                                              int64_t tail_from, double* __restrict__ partial) {
   typedef typename VecT<W>::T V;
   const int hc = ks / W;
@@ -266,20 +267,22 @@ __global__ void __launch_bounds__(TB) k_init(const double* __restrict__ F, const
     if (i >= tail_from) {  // rows preconditioned by their diagonal: all rows ("local"), the high-order rows ("multigrid")
       const double d = dinv[i];
       const V z = mk<W>(d * lo(f), d * hi(f));
-      reinterpret_cast<V*>(Z)[e] = z;
       reinterpret_cast<V*>(P)[i * (kps / W) + cp] = z;
       rz0 = fma(lo(f), lo(z), rz0); rz1 = fma(hi(f), hi(z), rz1);
+    } else {
+      reinterpret_cast<V*>(B0)[i * (kz / W) + cp] = f;
     }
   }
   flat_partials<W>(rr0, rr1, rz0, rz1, hc, partial, 2);
 }
 
-// x += alpha p ; r -= alpha q ; z = dinv r on rows >= tail_from ; partials [0] = r.r, [1] = r.z over those rows
+// r -= alpha q ; partials [0] = r.r, [1] = r.z over the rows >= tail_from, where z = dinv r is NOT stored (k_update_px
+// recomputes it from r); rows < tail_from: the new r also goes to the V-cycle's right-hand-side block B0 (row stride kz).
+// x += alpha p moved to k_update_px, which reads p anyway: this kernel touches neither P nor X.
 template <int W>
-__global__ void __launch_bounds__(TB) k_update_xr(double* __restrict__ X, double* __restrict__ R, const double* __restrict__ P,
-                                                  const double* __restrict__ Q, const double* __restrict__ dinv,
-                                                  double* __restrict__ Z, const double* __restrict__ scal, int ks, int kps,
-                                                  int64_t n, int64_t tail_from, double* __restrict__ partial) {
+__global__ void __launch_bounds__(TB) k_update_r(double* __restrict__ R, const double* __restrict__ Q, const double* __restrict__ dinv,
+                                                 double* __restrict__ B0, const double* __restrict__ scal, int ks, int kz,
+                                                 int64_t n, int64_t tail_from, double* __restrict__ partial) {
   typedef typename VecT<W>::T V;
   const int hc = ks / W;
   const int64_t T = (int64_t)gridDim.x * TB, gt = (int64_t)blockIdx.x * TB + threadIdx.x;
@@ -289,35 +292,35 @@ __global__ void __launch_bounds__(TB) k_update_xr(double* __restrict__ X, double
   double rr0 = 0.0, rr1 = 0.0, rz0 = 0.0, rz1 = 0.0;
   int64_t i = gt / hc;
   for (int64_t e = gt; e < total; e += T, i += di) {
-    const V p = reinterpret_cast<const V*>(P)[i * (kps / W) + cp];
     const V q = reinterpret_cast<const V*>(Q)[e];
-    const V x = reinterpret_cast<const V*>(X)[e];
     const V r = reinterpret_cast<const V*>(R)[e];
-    reinterpret_cast<V*>(X)[e] = mk<W>(fma(al0, lo(p), lo(x)), fma(al1, hi(p), hi(x)));
     const double s0 = fma(-al0, lo(q), lo(r)), s1 = fma(-al1, hi(q), hi(r));
     reinterpret_cast<V*>(R)[e] = mk<W>(s0, s1);
     rr0 = fma(s0, s0, rr0); rr1 = fma(s1, s1, rr1);
     if (i >= tail_from) {
       const double d = dinv[i];
-      const double z0 = d * s0, z1 = d * s1;
-      reinterpret_cast<V*>(Z)[e] = mk<W>(z0, z1);
-      rz0 = fma(s0, z0, rz0); rz1 = fma(s1, z1, rz1);
+      rz0 = fma(s0, d * s0, rz0); rz1 = fma(s1, d * s1, rz1);
+    } else {
+      reinterpret_cast<V*>(B0)[i * (kz / W) + cp] = mk<W>(s0, s1);
     }
   }
   flat_partials<W>(rr0, rr1, rz0, rz1, hc, partial, 2);
 }
 
-// partial [1] += r.z over rows [0, n): the rows preconditioned by the V-cycle (the others were summed by k_update_xr)
+// partial [1] += r.z over rows [0, n): the rows preconditioned by the V-cycle (z in Zv, row stride kz; the others were
+// summed by k_update_r / k_init)
 template <int W>
-__global__ void __launch_bounds__(TB) k_dot_rz(const double* __restrict__ R, const double* __restrict__ Z, int ks, int64_t n,
+__global__ void __launch_bounds__(TB) k_dot_rz(const double* __restrict__ R, const double* __restrict__ Zv, int ks, int kz, int64_t n,
                                                double* __restrict__ partial) {
   typedef typename VecT<W>::T V;
   const int hc = ks / W;
   const int64_t T = (int64_t)gridDim.x * TB, gt = (int64_t)blockIdx.x * TB + threadIdx.x;
-  const int64_t total = n * hc;
+  const int cp = (int)(gt % hc);
+  const int64_t total = n * hc, di = T / hc;
   double rz0 = 0.0, rz1 = 0.0;
-  for (int64_t e = gt; e < total; e += T) {
-    const V r = reinterpret_cast<const V*>(R)[e], z = reinterpret_cast<const V*>(Z)[e];
+  int64_t i = gt / hc;
+  for (int64_t e = gt; e < total; e += T, i += di) {
+    const V r = reinterpret_cast<const V*>(R)[e], z = reinterpret_cast<const V*>(Zv)[i * (kz / W) + cp];
     rz0 = fma(lo(r), lo(z), rz0); rz1 = fma(hi(r), hi(z), rz1);
   }
   __shared__ double sh[2][TB];
@@ -326,27 +329,40 @@ __global__ void __launch_bounds__(TB) k_dot_rz(const double* __restrict__ R, con
   if ((int)threadIdx.x < hc) {
     const int first = (int)((hc - (int)(((int64_t)blockIdx.x * TB) % hc) + (int)threadIdx.x) % hc);
     double t0 = 0.0, t1 = 0.0;
-    for (int i = first; i < TB; i += hc) { t0 += sh[0][i]; t1 += sh[1][i]; }
+    for (int i2 = first; i2 < TB; i2 += hc) { t0 += sh[0][i2]; t1 += sh[1][i2]; }
     const int64_t o = ((int64_t)blockIdx.x * 2 + 1) * KMAX + W * threadIdx.x;
     partial[o] += t0;
     if (W == 2) partial[o + 1] += t1;
   }
 }
 
-// p = z + beta p
+// x += alpha p ; p = z + beta p, with z = dinv r recomputed on the rows >= tail_from and read from the V-cycle's result
+// Zv (row stride kz) on the others: one pass over P serves both updates, and Z is never stored for the high-order rows.
 template <int W>
-__global__ void __launch_bounds__(TB) k_update_p(double* __restrict__ P, const double* __restrict__ Z,
-                                                 const double* __restrict__ scal, int ks, int kps, int64_t n) {
+__global__ void __launch_bounds__(TB) k_update_px(double* __restrict__ X, double* __restrict__ P, const double* __restrict__ R,
+                                                  const double* __restrict__ dinv, const double* __restrict__ Zv,
+                                                  const double* __restrict__ scal, int ks, int kps, int kz, int64_t n,
+                                                  int64_t tail_from) {
   typedef typename VecT<W>::T V;
   const int hc = ks / W;
   const int64_t T = (int64_t)gridDim.x * TB, gt = (int64_t)blockIdx.x * TB + threadIdx.x;
   const int cp = (int)(gt % hc);
   const int64_t total = n * hc, di = T / hc;
+  const double al0 = scal[S_ALPHA * KMAX + W * cp], al1 = (W == 2) ? scal[S_ALPHA * KMAX + W * cp + 1] : 0.0;
   const double be0 = scal[S_BETA * KMAX + W * cp], be1 = (W == 2) ? scal[S_BETA * KMAX + W * cp + 1] : 0.0;
   int64_t i = gt / hc;
   for (int64_t e = gt; e < total; e += T, i += di) {
     V* pp = reinterpret_cast<V*>(P) + i * (kps / W) + cp;
-    const V p = *pp, z = reinterpret_cast<const V*>(Z)[e];
+    const V p = *pp, x = reinterpret_cast<const V*>(X)[e];
+    reinterpret_cast<V*>(X)[e] = mk<W>(fma(al0, lo(p), lo(x)), fma(al1, hi(p), hi(x)));
+    V z;
+    if (i >= tail_from) {
+      const double d = dinv[i];
+      const V r = reinterpret_cast<const V*>(R)[e];
+      z = mk<W>(d * lo(r), d * hi(r));
+    } else {
+      z = reinterpret_cast<const V*>(Zv)[i * (kz / W) + cp];
+    }
     *pp = mk<W>(fma(be0, lo(p), lo(z)), fma(be1, hi(p), hi(z)));
   }
 }
@@ -436,25 +452,6 @@ __global__ void k_scal_beta(const double* __restrict__ partial, int nblk, double
       scal[S_BETA * KMAX + r] = 0.0;
     }
   }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Jacobi: dinv = 1/diag on free dofs, 0 on constrained
-// ------------------------------------------------------------------------------------------------
-__global__ void k_dinv(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
-                       const uint8_t* __restrict__ constrained, double* __restrict__ dinv, int64_t n) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double d = 0.0;
-  if (!constrained[i]) {
-    int64_t lo = rowptr[i], hi = rowptr[i + 1];
-    while (lo < hi) {
-      int64_t mid = (lo + hi) >> 1;
-      if (col[mid] < (int32_t)i) lo = mid + 1; else hi = mid;
-    }
-    if (lo < rowptr[i + 1] && col[lo] == (int32_t)i && val[lo] > 0.0) d = 1.0 / val[lo];
-  }
-  dinv[i] = d;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -558,9 +555,17 @@ void alloc_solver_state(Ctx* c, int nrhs) {
   cudaStream_t st = c->stream;
   const size_t n = (size_t)c->ndof * nrhs;
   c->F.ensure(n, st); c->X.ensure(n, st); c->R.ensure(n, st);
-  c->Z.ensure(n, st); c->Q.ensure(n, st);
-  // P alone gets a power-of-two row stride when the SELL SpMM gathers it (sell.cu): no gathered row straddles a line
-  c->pstride = (spmm_variant() >= 5 && nrhs >= 2 && (nrhs & 1) == 0) ? sell_pstride(nrhs) : nrhs;
+  c->Q.ensure(n, st);
+  // the rows preconditioned by the V-cycle (the vertex block) have their own right-hand-side / result blocks with an even
+  // row stride (amg.cu works on column pairs); the padding column of an odd count stays zero
+  c->kz = (nrhs + 1) & ~1;
+  c->B0.ensure((size_t)c->nv * c->kz, st); c->Zv.ensure((size_t)c->nv * c->kz, st);
+  CK(cudaMemsetAsync(c->B0.p, 0, (size_t)c->nv * c->kz * sizeof(double), st));
+  CK(cudaMemsetAsync(c->Zv.p, 0, (size_t)c->nv * c->kz * sizeof(double), st));
+  // P alone gets a power-of-two row stride when the SELL SpMM gathers it (sell.cu): no gathered row straddles a line.
+  // The element-wise product stages whole rows of P once per batch: it takes the plain stride.
+  const bool ebe = ebe_eligible(c) && nrhs <= ebe_max_rhs();
+  c->pstride = (!ebe && spmm_variant() >= 5 && nrhs >= 2 && (nrhs & 1) == 0) ? sell_pstride(nrhs) : nrhs;
   c->P.ensure((size_t)c->ndof * c->pstride, st);
   if (c->pstride != nrhs) CK(cudaMemsetAsync(c->P.p, 0, (size_t)c->ndof * c->pstride * sizeof(double), st));
   c->partial.ensure((size_t)std::max(vec_grid(c, nrhs), c->num_sms * 192) * 2 * KMAX, st);  // room for any SpMM grid (sell.cu caps its own)
@@ -579,8 +584,12 @@ int spmm_variant() {
   return v;
 }
 
-// even (the SpMM gathers two right-hand sides per 16-byte load); the extra column of an odd count has b = 0
-int solver_stride(int nrhs) { return (nrhs > 1 && spmm_variant() >= 4) ? ((nrhs + 1) & ~1) : nrhs; }
+// CSR / SELL kernels: even (they gather two right-hand sides per 16-byte load); the extra column of an odd count has
+// b = 0.  Element-wise product (ebe.cu): exactly nrhs -- no dead column in any vector pass.
+int solver_stride(const Ctx* c, int nrhs) {
+  if (ebe_eligible(c) && nrhs <= ebe_max_rhs()) return nrhs;
+  return (nrhs > 1 && spmm_variant() >= 4) ? ((nrhs + 1) & ~1) : nrhs;
+}
 int spmm_blocks(Ctx* c, int ks) { return spmm_grid(c, ks); }
 
 void launch_spmm(Ctx* c, const double* P, double* Q, int nrhs) {
@@ -634,6 +643,7 @@ void launch_spmm(Ctx* c, const double* P, double* Q, int nrhs) {
 // after alloc_solver_state / the right-hand sides are known: make sure the matrix copy the chosen SpMM kernel reads exists
 void spmm_prepare(Ctx* c) {
   if (!c->have_matrix || use_ebe(c, c->P.p)) return;
+  ensure_values(c);  // the CSR / SELL kernels read the assembled matrix
   if (spmm_variant() >= 5 && c->pstride >= 2 && !c->have_sell) sell_build(c);
 }
 
@@ -645,8 +655,8 @@ int spmm_kind(Ctx* c) {
 
 void launch_vector_updates(Ctx* c, int nrhs) {
   const int grid = vec_grid(c, nrhs);
-  DISPATCH_W(nrhs, (k_update_xr<W><<<grid, TB, 0, c->stream>>>(c->X.p, c->R.p, c->P.p, c->Q.p, c->dinv.p, c->Z.p, c->scal.p, nrhs, c->pstride, c->ndof, (int64_t)0, c->partial.p)));
-  DISPATCH_W(nrhs, (k_update_p<W><<<grid, TB, 0, c->stream>>>(c->P.p, c->Z.p, c->scal.p, nrhs, c->pstride, c->ndof)));
+  DISPATCH_W(nrhs, (k_update_r<W><<<grid, TB, 0, c->stream>>>(c->R.p, c->Q.p, c->dinv.p, c->B0.p, c->scal.p, nrhs, c->kz, c->ndof, (int64_t)0, c->partial.p)));
+  DISPATCH_W(nrhs, (k_update_px<W><<<grid, TB, 0, c->stream>>>(c->X.p, c->P.p, c->R.p, c->dinv.p, c->Zv.p, c->scal.p, nrhs, c->pstride, c->kz, c->ndof, (int64_t)0)));
   c->launches += 2;
   CK(cudaGetLastError());
 }
@@ -655,13 +665,17 @@ void precond_setup(Ctx* c, int kind) {
   if (!c->have_matrix) FAIL(REMO_ERR_STATE, "remo_precond_setup: no matrix (call remo_assemble first)");
   if (kind != REMO_PRECOND_LOCAL && kind != REMO_PRECOND_MULTIGRID) FAIL(REMO_ERR_ARG, "remo_precond_setup: unknown preconditioner kind %d", kind);
   StageTimer timer(c, ST_PRECOND);
+  // diag(A) and the V-cycle's vertex block come straight from the element metrics (assemble.cu): no assembled matrix
   c->dinv.ensure(c->ndof, c->stream);
-  LAUNCH(c, k_dinv, grid_for(c->ndof, TB), TB, 0, c->rowptr.p, c->col.p, c->val.p, c->constrained.p, c->dinv.p, c->ndof);
+  diag_from_elements(c, c->dinv.p);
   if (kind == REMO_PRECOND_MULTIGRID) amg_setup(c);
-  // order-2 tets: the element-wise product needs no second copy of the matrix; the SELL copy is made on demand
-  // (spmm_prepare) if a block wider than ebe.cu takes shows up
+  // order-2 tets: the element-wise product needs no copy of the matrix at all; the CSR values and the SELL copy are made
+  // on demand (spmm_prepare) if a block wider than ebe.cu takes shows up
   if (ebe_eligible(c)) { if (!c->have_ebe) ebe_build(c); }
-  else if (spmm_variant() >= 5 && !c->have_sell) sell_build(c);
+  else {
+    ensure_values(c);
+    if (spmm_variant() >= 5 && !c->have_sell) sell_build(c);
+  }
   c->pkind = kind;
 }
 
@@ -672,7 +686,7 @@ void rhs_point_sources(Ctx* c, int nrhs, const int64_t* src_ptr, const double* s
   cudaStream_t st = c->stream;
   // row stride of the vector blocks: even (the SpMM gathers two right-hand sides per 16-byte load); the extra column
   // of an odd count has b = 0 and is frozen from the first iteration
-  const int ks = solver_stride(nrhs);
+  const int ks = solver_stride(c, nrhs);
   alloc_solver_state(c, ks);
   c->nrhs_user = nrhs;
   std::vector<int64_t> hp(nrhs + 1);
@@ -711,13 +725,13 @@ int solve(Ctx* c, double rtol, int maxit, int* iters, double* relres) {
   const int jac = (c->pkind == REMO_PRECOND_LOCAL) ? 1 : 0;
   const int64_t tail = jac ? 0 : c->nv;  // rows >= tail: z = D^-1 r fused into the vector kernels; rows < tail: V-cycle
 
-  const int kps = c->pstride;
-  DISPATCH_W(k, (k_init<W><<<vg, TB, 0, st>>>(c->F.p, c->constrained.p, c->dinv.p, c->X.p, c->R.p, c->Z.p, c->P.p, k, kps, n, tail, c->partial.p)));
+  const int kps = c->pstride, kz = c->kz;
+  DISPATCH_W(k, (k_init<W><<<vg, TB, 0, st>>>(c->F.p, c->constrained.p, c->dinv.p, c->X.p, c->R.p, c->B0.p, c->P.p, k, kps, kz, n, tail, c->partial.p)));
   c->launches++;
   if (!jac) {
-    amg_apply(c, c->R.p, c->Z.p, k);
-    DISPATCH_W(k, (k_dot_rz<W><<<vg, TB, 0, st>>>(c->R.p, c->Z.p, k, tail, c->partial.p)));
-    CK(cudaMemcpy2DAsync(c->P.p, (size_t)kps * sizeof(double), c->Z.p, (size_t)k * sizeof(double), (size_t)k * sizeof(double), (size_t)tail, cudaMemcpyDeviceToDevice, st));
+    amg_apply(c, c->B0.p, c->Zv.p, kz);
+    DISPATCH_W(k, (k_dot_rz<W><<<vg, TB, 0, st>>>(c->R.p, c->Zv.p, k, kz, tail, c->partial.p)));
+    CK(cudaMemcpy2DAsync(c->P.p, (size_t)kps * sizeof(double), c->Zv.p, (size_t)kz * sizeof(double), (size_t)k * sizeof(double), (size_t)tail, cudaMemcpyDeviceToDevice, st));
     c->launches++;
   }
   k_scal_init<<<1, 1024, 0, st>>>(c->partial.p, vg, c->scal.p, c->iters_d.p, k, rtol, kp);
@@ -744,14 +758,14 @@ int solve(Ctx* c, double rtol, int maxit, int* iters, double* relres) {
     launch_spmm(c, c->P.p, c->Q.p, k);
     if (c->prof) CK(cudaEventRecord(c->prof_ev[pe + 1], st));
     k_scal_alpha<<<1, 1024, 0, st>>>(c->partial.p, sg, c->scal.p, kp);
-    DISPATCH_W(k, (k_update_xr<W><<<vg, TB, 0, st>>>(c->X.p, c->R.p, c->P.p, c->Q.p, c->dinv.p, c->Z.p, c->scal.p, k, kps, n, tail, c->partial.p)));
+    DISPATCH_W(k, (k_update_r<W><<<vg, TB, 0, st>>>(c->R.p, c->Q.p, c->dinv.p, c->B0.p, c->scal.p, k, kz, n, tail, c->partial.p)));
     if (!jac) {
-      amg_apply(c, c->R.p, c->Z.p, k);
-      DISPATCH_W(k, (k_dot_rz<W><<<vg, TB, 0, st>>>(c->R.p, c->Z.p, k, tail, c->partial.p)));
+      amg_apply(c, c->B0.p, c->Zv.p, kz);
+      DISPATCH_W(k, (k_dot_rz<W><<<vg, TB, 0, st>>>(c->R.p, c->Zv.p, k, kz, tail, c->partial.p)));
       c->launches++;
     }
     k_scal_beta<<<1, 1024, 0, st>>>(c->partial.p, vg, c->scal.p, c->iters_d.p, kp);
-    DISPATCH_W(k, (k_update_p<W><<<vg, TB, 0, st>>>(c->P.p, c->Z.p, c->scal.p, k, kps, n)));
+    DISPATCH_W(k, (k_update_px<W><<<vg, TB, 0, st>>>(c->X.p, c->P.p, c->R.p, c->dinv.p, c->Zv.p, c->scal.p, k, kps, kz, n, tail)));
     c->launches += 4;
   };
 
@@ -760,7 +774,7 @@ int solve(Ctx* c, double rtol, int maxit, int* iters, double* relres) {
   int64_t launches_per_iter = 0;
   const bool graphs = c->use_graph && !c->prof && getenv("REMO_NO_GRAPH") == nullptr;
   if (graphs) {
-    if (!jac) amg_prepare(c, k);  // no allocation may happen inside the capture
+    if (!jac) amg_prepare(c, kz);  // no allocation may happen inside the capture
     const int64_t l0 = c->launches;
     CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     try {

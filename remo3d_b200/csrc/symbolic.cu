@@ -316,7 +316,7 @@ void space_build(Ctx* c, int order) {
   c->nlf = (dim == 3) ? 4 : 1;
   c->npair = nvl * (nvl + 1) / 2;
   c->nld = nvl + c->nle * (order - 1) + (order == 3 ? c->nlf : 0);
-  c->have_space = c->have_matrix = c->have_sell = c->have_ebe = false;
+  c->have_space = c->have_matrix = c->have_sell = c->have_ebe = c->have_pattern = c->have_values = false;
   c->pkind = -1;
 
   // 1. sorted element vertices
@@ -325,9 +325,7 @@ void space_build(Ctx* c, int order) {
 
   // scratch slots: 0 keys, 1 sorted keys, 2 payload, 3 sorted payload, 4 flags, 5 scan, 6/7 candidate columns
   const int64_t nadj = nt * c->nld;
-  const int64_t ncand = nadj * c->nld;
   if (nadj >= (int64_t)1 << 32) FAIL(REMO_ERR_ARG, "remo_space_build: mesh too large (nt*nld >= 2^32)");
-  if (ncand >= (int64_t)1 << 31) FAIL(REMO_ERR_ARG, "remo_space_build: %lld candidate entries exceed the 2^31 limit of the pattern builder", (long long)ncand);
   const int64_t nkeys = std::max<int64_t>(nt * c->nle, nt * 4);
   uint64_t* k64 = scratch<uint64_t>(c, 0, std::max<int64_t>(nkeys, (nadj + 1) / 2));
   uint64_t* k64s = scratch<uint64_t>(c, 1, std::max<int64_t>(nkeys, (nadj + 1) / 2));
@@ -392,7 +390,21 @@ void space_build(Ctx* c, int order) {
   c->adj_ptr.ensure(c->ndof + 1, st);
   LAUNCH(c, k_adj_ptr, grid_for(nadj + 1, TB), TB, 0, akeys, nadj, c->ndof, c->adj_ptr.p);
 
-  // 6. CSR pattern: per row the sorted distinct dofs of the adjacent elements (k_pattern_*)
+  c->have_space = true;
+  c->have_pattern = false;
+  c->nnz = 0;
+  // 6. CSR pattern: only when somebody needs the assembled matrix (pattern_build); the element-wise PCG path never does
+  if (!c->lazy_matrix) pattern_build(c);
+}
+
+// CSR pattern of the whole matrix: per row the sorted distinct dofs of the adjacent elements (k_pattern_*).  Idempotent.
+void pattern_build(Ctx* c) {
+  if (!c->have_space) FAIL(REMO_ERR_STATE, "no space (call remo_space_build first)");
+  if (c->have_pattern) return;
+  cudaStream_t st = c->stream;
+  SpaceView sview = make_view(c);
+  const int64_t ncand = c->nadj * c->nld;
+  if (ncand >= (int64_t)1 << 31) FAIL(REMO_ERR_ARG, "CSR pattern: %lld candidate entries exceed the 2^31 limit of the pattern builder", (long long)ncand);
   {
     int32_t* seg = scratch<int32_t>(c, 6, ncand);          // row d's columns at the head of [adj_ptr[d] * nld, ...)
     int32_t* count = scratch<int32_t>(c, 4, c->ndof + 1);
@@ -400,21 +412,13 @@ void space_build(Ctx* c, int order) {
     int64_t* incl = scratch<int64_t>(c, 7, c->ndof + 1);
     int* flags = scratch<int>(c, 8, 4);
     CK(cudaMemsetAsync(flags, 0, 4 * sizeof(int), st));
-    static bool attr_w = false;
-    if (!attr_w) {
-      CK(cudaFuncSetAttribute(k_pattern_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * WARP_CAP * (int)sizeof(uint32_t)));
-      attr_w = true;
-    }
+    allow_max_smem(k_pattern_warp, c->device);  // per (kernel, device), see ctx.cuh
     LAUNCH(c, k_pattern_warp, c->num_sms * 6, 256, 8 * WARP_CAP * sizeof(uint32_t), sview, c->adj_ptr.p, c->adj.p, seg, count, flags);
     int hf[2] = {0, 0};
     CK(cudaMemcpyAsync(hf, flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (hf[0] > 0) {  // rows with more than WARP_CAP candidates: one CTA per row
-      static bool attr = false;
-      if (!attr) {
-        CK(cudaFuncSetAttribute(k_pattern_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, CTA_CAP * (int)sizeof(uint32_t)));
-        attr = true;
-      }
+      allow_max_smem(k_pattern_cta, c->device);
       LAUNCH(c, k_pattern_cta, c->num_sms, 256, CTA_CAP * sizeof(uint32_t), sview, c->adj_ptr.p, c->adj.p, seg, count, flags + 1);
       CK(cudaMemcpyAsync(hf, flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
@@ -437,8 +441,54 @@ void space_build(Ctx* c, int order) {
     LAUNCH(c, k_count_to_ptr, grid_for(c->ndof + 1, TB), TB, 0, incl, c->ndof, c->rowptr.p);
     LAUNCH(c, k_pattern_copy, c->num_sms * 8, 256, 0, c->adj_ptr.p, c->nld, seg, c->rowptr.p, c->ndof, c->col.p);
   }
-  c->have_space = true;
+  c->have_pattern = true;
 }
+
+namespace {
+
+__global__ void k_vv_keys(const uint64_t* __restrict__ edge_keys, int64_t ne, uint64_t* __restrict__ rev) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e < ne) rev[e] = (edge_keys[e] << 32) | (edge_keys[e] >> 32);  // (b, a): neighbours with a smaller number, by row b
+}
+
+// row a of the vertex graph: [neighbours c < a, ascending | a | neighbours b > a, ascending]; its first entry sits at
+// a + (edges whose smaller vertex is < a) + (edges whose larger vertex is < a) -- no scan needed
+__global__ void k_vv_pattern(const uint64_t* __restrict__ edge_keys, const uint64_t* __restrict__ rev, int64_t ne, int64_t nv,
+                             int64_t* __restrict__ rowptr, int32_t* __restrict__ col) {
+  int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (a > nv) return;
+  const int64_t u0 = lower_bound_u64(edge_keys, ne, (uint64_t)a << 32), l0 = lower_bound_u64(rev, ne, (uint64_t)a << 32);
+  const int64_t o = a + u0 + l0;
+  rowptr[a] = o;
+  if (a == nv) return;
+  const int64_t u1 = lower_bound_u64(edge_keys, ne, (uint64_t)(a + 1) << 32), l1 = lower_bound_u64(rev, ne, (uint64_t)(a + 1) << 32);
+  int64_t w = o;
+  for (int64_t j = l0; j < l1; j++) col[w++] = (int32_t)(rev[j] & 0xffffffffu);
+  col[w++] = (int32_t)a;
+  for (int64_t j = u0; j < u1; j++) col[w++] = (int32_t)(edge_keys[j] & 0xffffffffu);
+}
+
+}  // namespace
+
+// CSR pattern of the vertex block (= the vertex graph of the mesh + the diagonal) from the edge list.  Returns its nnz.
+int64_t vertex_block_pattern(Ctx* c, DBuf<int64_t>& rowptr, DBuf<int32_t>& col) {
+  cudaStream_t st = c->stream;
+  const int64_t ne = c->ne, nv = c->nv, nnz = nv + 2 * ne;
+  uint64_t* rev = scratch<uint64_t>(c, 0, ne);
+  uint64_t* revs = scratch<uint64_t>(c, 1, ne);
+  LAUNCH(c, k_vv_keys, grid_for(ne, TB), TB, 0, c->edge_keys.p, ne, rev);
+  size_t bytes = 0;
+  const int end_bit = std::min(64, 32 + bits_for((uint64_t)nv));
+  CK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, rev, revs, ne, 0, end_bit, st));
+  c->tmp.ensure(bytes, st);
+  CK(cub::DeviceRadixSort::SortKeys(c->tmp.p, bytes, rev, revs, ne, 0, end_bit, st));
+  c->launches += 2;
+  rowptr.ensure(nv + 1, st);
+  col.ensure(nnz, st);
+  LAUNCH(c, k_vv_pattern, grid_for(nv + 1, TB), TB, 0, c->edge_keys.p, revs, ne, nv, rowptr.p, col.p);
+  return nnz;
+}
+
 
 void topology_get(Ctx* c, int32_t* edges, int32_t* faces, int32_t* elem_edges, int32_t* elem_faces) {
   if (!c->have_space) FAIL(REMO_ERR_STATE, "remo_topology_get: no space (call remo_space_build first)");

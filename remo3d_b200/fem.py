@@ -45,8 +45,12 @@ class FESpace:
         self.ctx = ctx or default_context()
         flags = mesh.dirichlet_flags(dirichlet)
         self.ctx.mesh_set(mesh.dim, mesh.points, mesh.elems, mesh.mat, mesh.bfacets, flags, mesh.axis_vertices())
-        self.ndof, self.nnz = self.ctx.space_build(self.order)
+        self.ndof, _ = self.ctx.space_build(self.order)
         self.generation = _next_generation(self.ctx)
+
+    @property
+    def nnz(self):
+        return self.ctx.nnz
 
     def FreeDofs(self):
         return ~self.ctx.dirichlet()

@@ -16,13 +16,13 @@ DIRICHLET = "dirichlet_boundary"  # worker.py:90
 def solve_task(ctx, mesh, sigma, flat, order=3, preconditioner="multigrid", rtol=1e-10, maxit=1000):
     """One mesh task on one context -> (Ra per log point, per-task record).  Raises on failure."""
     ctx.mesh_set(mesh.dim, mesh.points, mesh.elems, mesh.mat, mesh.bfacets, mesh.dirichlet_flags(DIRICHLET), mesh.axis_vertices())
-    ndof, nnz = ctx.space_build(order)
+    ndof, _ = ctx.space_build(order)  # the CSR pattern (and its nnz) is built only on demand: not on this path
     ctx.assemble(np.asarray(sigma, dtype=np.float64))
     ctx.precond_setup(preconditioner)
     ctx.rhs_point_sources(flat["src_ptr"], flat["src_z"], flat["src_fac"])
     iters, relres = ctx.solve(rtol=rtol, maxit=maxit)
     ra = ctx.apparent_resistivity(flat["pt_rhs"], flat["pt_z0"], flat["pt_z1"], flat["pt_k"], flat["scale"])
-    rec = {"ndof": ndof, "nnz": nnz, "iters": iters.tolist(), "relres": float(relres.max())}
+    rec = {"ndof": ndof, "iters": iters.tolist(), "relres": float(relres.max())}
     rec.update(ctx.stage_times())
     return ra, rec
 

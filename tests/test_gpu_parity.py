@@ -124,6 +124,119 @@ def test_multigrid_preconditioner_same_solution(ctx, order):
     print("order", order, "iterations jacobi", it_jac.tolist(), "multigrid", it_mg.tolist())
 
 
+@pytest.mark.parametrize("dim,order", [(3, 1), (3, 2), (3, 3), (2, 2), (2, 3)])
+def test_preconditioner_pieces_come_from_the_elements(ctx, dim, order):
+    """remo_precond_setup never reads the assembled matrix: diag(A) and the vertex block of the V-cycle are gathered
+    from the element metrics.  Both must equal the corresponding entries of the oracle's matrix (the vertex block
+    bit-identically to the library's own CSR export, which is built afterwards, on demand)."""
+    if dim == 3:
+        mesh, sigma = helpers.ball_case()[:2]
+        flags = mesh.dirichlet_flags("dirichlet_boundary")
+    else:
+        mesh, sigma = helpers.disc_case()[:2]
+        flags = mesh.dirichlet_flags([2])
+    ctx.mesh_set(dim, mesh.points, mesh.elems, mesh.mat, mesh.bfacets, flags, mesh.axis_vertices())
+    ndof, nnz0 = ctx.space_build(order)
+    assert nnz0 == 0  # lazy: no CSR pattern yet
+    ctx.assemble(sigma)
+    ctx.precond_setup("multigrid")
+    dinv, (rp, cl, vl), levels = ctx.precond_get(vertex_block=True)
+    space = fo.Space(mesh.nv, mesh.elems, order, dim)
+    A = fo.assemble(mesh.points, space, sigma, mesh.mat)
+    con = space.dirichlet_dofs(mesh.bfacets, flags)
+    want = np.where(con, 0.0, 1.0 / A.diagonal())
+    np.testing.assert_allclose(dinv, want, rtol=1e-13, atol=0)
+    Avv = A[: mesh.nv][:, : mesh.nv].tocsr()
+    Avv.sort_indices()
+    np.testing.assert_array_equal(rp, Avv.indptr)
+    np.testing.assert_array_equal(cl, Avv.indices)
+    assert np.linalg.norm(vl - Avv.data) <= 1e-12 * np.linalg.norm(Avv.data)
+    # ... and bit-identical to the same entries of the library's own matrix
+    rowptr, col, val = ctx.matrix()
+    G = sp.csr_matrix((val, col, rowptr), shape=(ndof, ndof))[: mesh.nv][:, : mesh.nv].tocsr()
+    G.sort_indices()
+    assert np.array_equal(G.data, vl)
+    assert np.array_equal(np.where(con, 0.0, 1.0 / sp.csr_matrix((val, col, rowptr), shape=(ndof, ndof)).diagonal()), dinv)
+    assert levels[0] == (mesh.nv, Avv.nnz) and all(a[0] > b[0] for a, b in zip(levels, levels[1:])) and levels[-1][0] <= 256
+    print("levels", levels)
+
+
+def test_eager_matrix_option_gives_the_same_matrix(ctx):
+    mesh, sigma = helpers.ball_case()[:2]
+    _setup(ctx, mesh, 2)
+    ctx.assemble(sigma)
+    lazy = ctx.matrix()
+    ctx.set_option("lazy_matrix", 0)
+    try:
+        ctx.mesh_set(3, mesh.points, mesh.elems, mesh.mat, mesh.bfacets, mesh.dirichlet_flags("dirichlet_boundary"), mesh.axis_vertices())
+        ndof, nnz = ctx.space_build(2)
+        assert nnz == lazy[1].shape[0]
+        ctx.assemble(sigma)
+        eager = ctx.matrix()
+    finally:
+        ctx.set_option("lazy_matrix", 1)
+    for a, b in zip(lazy, eager):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("opts", [{"amg_agg": 0}, {"amg_agg": 1, "amg_passes": 3}, {"amg_agg": 1, "amg_passes": 2}, {"amg_agg": 1, "amg_passes": 1, "amg_rounds": 1}])
+def test_aggregation_variants_same_solution(ctx, opts):
+    """The V-cycle hierarchy (Morton-rank aggregates of round 1, strength-based pairwise aggregation with 1-3 passes) only
+    changes the preconditioner: same solution, and the pairwise aggregates never need more iterations than 1.15 x Morton's."""
+    mesh, sigma, flat, _ = helpers.ball_case(h_electrode=0.05, h_axis=0.2, grading=0.45)
+    ref = fo.solve_task(mesh.points, mesh.elems, mesh.mat, sigma, mesh.bfacets, mesh.dirichlet_flags("dirichlet_boundary"), 2, flat)
+    _setup(ctx, mesh, 2)
+    ctx.assemble(sigma)
+    ctx.rhs_point_sources(flat["src_ptr"], flat["src_z"], flat["src_fac"])
+    its = {}
+    try:
+        for name, o in (("morton", {"amg_agg": 0}), ("this", opts)):
+            for k, v in o.items():
+                ctx.set_option(k, v)
+            ctx.precond_setup("multigrid")
+            it, relres = ctx.solve(rtol=1e-10, maxit=3000)
+            assert (relres <= 1e-10).all()
+            its[name] = int(it.max())
+            ra = ctx.apparent_resistivity(flat["pt_rhs"], flat["pt_z0"], flat["pt_z1"], flat["pt_k"], flat["scale"])
+            np.testing.assert_allclose(ra, ref["ra"], rtol=1e-6)
+            print(name, o, "iterations", it.tolist(), "levels", ctx.precond_get()[2])
+    finally:
+        for k, v in (("amg_agg", 1), ("amg_passes", 3), ("amg_rounds", 4)):
+            ctx.set_option(k, v)
+    assert its["this"] <= 1.15 * its["morton"] + 2, its
+
+
+def test_mesh_after_the_sliver_pass_matches_oracle(ctx):
+    """bench.py's meshes go through meshgen.half_ball_mesh(improve=N) (sliver pass): the path on such a mesh against the
+    oracle -- numbering, matrix, Ra (both preconditioners)."""
+    from remo3d_b200 import meshgen, planner, tools as tl
+    from remo3d_b200.mesh import Mesh
+
+    params, sec = tl.set_tools_parameters(["A2.0M0.5N", "N0.5M2.0A", "B5.7A0.4M", "M4.0A0.5B"])
+    _, tasks = planner.prepare_simulation_depths_and_tasks(params, sec, np.arange(0, 100, 0.1), 5)
+    task = tasks[len(tasks) // 2]
+    flat = planner.flatten_task(task, params, three_d=True)
+    material = meshgen.layered_material([-1.0, 1.5], dip_rad=np.deg2rad(30.0), borehole_radius=0.1, inclusion=((3.0, 2.0, 1.0), 1.5))
+    m = meshgen.half_ball_mesh(50.0, task[1][0], material=material, h_electrode=0.08, h_axis=0.3, grading=0.55, h_max=6.0, seed=0, improve=3)
+    mesh = Mesh(m["points"], m["elems"], m["mat"], m["bfacets"], m["bc"], m["bc_names"])
+    sigma = [1 / 1.0, 1 / 10.0, 1 / 100.0, 1 / 10.0, 1 / 2.0]
+    flags = mesh.dirichlet_flags("dirichlet_boundary")
+    ref = fo.solve_task(mesh.points, mesh.elems, mesh.mat, sigma, mesh.bfacets, flags, 2, flat)
+    _setup(ctx, mesh, 2)
+    ctx.assemble(sigma)
+    rowptr, col, val = ctx.matrix()
+    np.testing.assert_array_equal(rowptr, ref["A"].indptr)
+    np.testing.assert_array_equal(col, ref["A"].indices)
+    assert np.linalg.norm(val - ref["A"].data) <= 1e-12 * np.linalg.norm(ref["A"].data)
+    for pre in ("multigrid", "local"):
+        ctx.precond_setup(pre)
+        ctx.rhs_point_sources(flat["src_ptr"], flat["src_z"], flat["src_fac"])
+        it, relres = ctx.solve(rtol=1e-10, maxit=20000)
+        assert (relres <= 1e-10).all()
+        ra = ctx.apparent_resistivity(flat["pt_rhs"], flat["pt_z0"], flat["pt_z1"], flat["pt_k"], flat["scale"])
+        np.testing.assert_allclose(ra, ref["ra"], rtol=1e-6)
+
+
 def test_homogeneous_ball_gives_rho(ctx):
     """Known answer: homogeneous medium -> Ra == rho for every tool, up to discretisation error."""
     mesh, sigma, flat, _ = helpers.ball_case(h_electrode=0.03, h_axis=0.12, grading=0.4, layered=False)
@@ -321,6 +434,7 @@ def test_pattern_of_a_high_valence_vertex(ctx, order):
         # a 3600-entry row (order 3, 516 tets around one vertex) must fail loudly, not silently
         with pytest.raises(_cabi.RemoError, match="row buffer"):
             ctx.assemble(sigma)
+            ctx.matrix()  # the CSR values are gathered on demand: the limit shows when somebody asks for them
         return
     ctx.assemble(sigma)
     val = ctx.matrix()[2]

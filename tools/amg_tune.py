@@ -14,7 +14,7 @@ task, flat = bench.make_task()
 m = bench.make_mesh(a.size, task, print)
 ctx = _cabi.Context(0)
 ctx.mesh_set(3, m["points"], m["elems"], m["mat"], m["bfacets"], m["bdir"], m["axis"])
-ndof, nnz = ctx.space_build(a.order)
+ndof, _ = ctx.space_build(a.order); nnz = ctx.nnz
 ctx.assemble(bench.SIGMA)
 ctx.rhs_point_sources(flat["src_ptr"], flat["src_z"], flat["src_fac"])
 print("ndof", ndof, "nnz", nnz)

@@ -14,7 +14,7 @@ flat = planner.flatten_task(tasks[len(tasks) // 2], params, three_d=True)
 ctx = _cabi.Context(0)
 for rep in range(2):
     ctx.mesh_set(3, m["points"], m["elems"], m["mat"], m["bfacets"], m["bdir"], m["axis"])
-    ndof, nnz = ctx.space_build(2)
+    ndof, _ = ctx.space_build(2); nnz = ctx.nnz
     ctx.assemble(SIGMA)
     ctx.precond_setup("multigrid")
     ctx.rhs_point_sources(flat["src_ptr"], flat["src_z"], flat["src_fac"])

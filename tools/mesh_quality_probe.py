@@ -26,7 +26,7 @@ for imp in rounds:
     if ctx is None:
         ctx = _cabi.Context(0)
     ctx.mesh_set(3, mesh.points, mesh.elems, mesh.mat, mesh.bfacets, mesh.dirichlet_flags("dirichlet_boundary"), mesh.axis_vertices())
-    ndof, nnz = ctx.space_build(2)
+    ndof, _ = ctx.space_build(2); nnz = ctx.nnz
     ctx.assemble(SIGMA)
     ctx.precond_setup("multigrid")
     ctx.rhs_point_sources(flat["src_ptr"], flat["src_z"], flat["src_fac"])
