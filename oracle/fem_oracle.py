@@ -420,6 +420,61 @@ def jacobi_pcg(A, f, constrained, rtol=1e-10, maxit=100000):
     return x, it, float(np.sqrt(r @ r) / bnorm)
 
 
+def two_level_pcg(A, F, constrained, nv, rtol=1e-10, maxit=5000):
+    """PCG with the reference's DEFAULT preconditioner, `ngs.Preconditioner(a, "multigrid")`
+    (`remo3d.py:82`, `ngsolve_functions.py:46`).  On a single-level mesh NGSolve's multigrid is a two-level method [NGS]:
+    an exact sparse factorisation of the lowest-order (P1) problem plus a smoother on the high-order dofs.  In the
+    hierarchical basis the P1 matrix is the leading nv x nv block, so the restatement is
+        z_vertex = A_vv^-1 r_vertex   (sparse LU of the free vertex block, factorised once per mesh)
+        z_high   = D^-1 r_high        (Jacobi on the edge / face dofs)
+    applied additively (symmetric, positive definite -> plain PCG).  All columns of F advance in lock-step with their own
+    alpha / beta (a converged column is frozen), zero start, stop on ||r||_2 <= rtol ||b||_2 per column.
+    Returns (U, iterations per column, relres per column)."""
+    free = ~np.asarray(constrained, dtype=bool)
+    F = np.asarray(F, dtype=np.float64)
+    if F.ndim == 1:
+        F = F[:, None]
+    B = np.where(free[:, None], F, 0.0)
+    fv = np.nonzero(free[:nv])[0]
+    lu = spla.splu(A[fv][:, fv].tocsc())
+    d = A.diagonal()
+    dinv = np.where(free & (d > 0), 1.0 / np.where(d != 0, d, 1.0), 0.0)
+
+    def precond(R):
+        Z = dinv[:, None] * R
+        Z[fv] = lu.solve(np.ascontiguousarray(R[fv]))
+        return Z
+
+    k = B.shape[1]
+    X = np.zeros_like(B)
+    R = B.copy()
+    Z = precond(R)
+    P = Z.copy()
+    rz = np.einsum("ij,ij->j", R, Z)
+    bb = np.einsum("ij,ij->j", B, B)
+    active = bb > 0
+    iters = np.zeros(k, dtype=np.int64)
+    rr = bb.copy()
+    for _ in range(maxit):
+        if not active.any():
+            break
+        Q = A @ P
+        Q[~free] = 0.0
+        pq = np.einsum("ij,ij->j", P, Q)
+        alpha = np.where(active & (pq > 0), rz / np.where(pq != 0, pq, 1.0), 0.0)
+        X += P * alpha
+        R -= Q * alpha
+        rr = np.einsum("ij,ij->j", R, R)
+        iters += active
+        active = active & (rr > rtol * rtol * bb)
+        Z = precond(R)
+        rzn = np.einsum("ij,ij->j", R, Z)
+        beta = np.where(active, rzn / np.where(rz != 0, rz, 1.0), 0.0)
+        P = Z + P * beta
+        rz = rzn
+    return X, iters, np.sqrt(rr / np.where(bb > 0, bb, 1.0))
+
+
 def apparent_resistivity(axis, u, k, z0, z1=None, scale=1.0):
     """worker.py:117-131: |K (u(z1) - u(z0))| with two potential electrodes (ascending z),
     |K u(z0)| with one; `scale` = 0.5 on the 3D half-ball."""
@@ -428,7 +483,7 @@ def apparent_resistivity(axis, u, k, z0, z1=None, scale=1.0):
     return abs(k * (sample_axis(axis, u, z1) - sample_axis(axis, u, z0))) * scale
 
 
-def solve_task(points, elems, mat, sigma, bfacets, bflag, order, flat, dim=3, solver="auto"):
+def solve_task(points, elems, mat, sigma, bfacets, bflag, order, flat, dim=3, solver="auto", rtol=1e-13):
     """One mesh task end to end: assemble once, all right-hand sides, all log points.
     `flat` is the dict produced by remo3d_b200.planner.flatten_task (plain arrays)."""
     space = Space(points.shape[0], elems, order, dim)
@@ -442,12 +497,15 @@ def solve_task(points, elems, mat, sigma, bfacets, bflag, order, flat, dim=3, so
         F[:, r] = point_source_rhs(axis, space.ndof, flat["src_z"][lo:hi], flat["src_fac"][lo:hi])
     if solver == "auto":  # sparse LU fill-in explodes on 3D high-order systems
         solver = "direct" if space.ndof <= 30000 else "pcg"
+    iters = None
     if solver == "direct":
         U = solve_direct(A, F, con)
+    elif solver == "multigrid":  # the reference's default preconditioner, all right-hand sides in one block
+        U, iters, _ = two_level_pcg(A, F, con, points.shape[0], rtol=rtol)
     else:
-        U = np.stack([jacobi_pcg(A, F[:, r], con, rtol=1e-13)[0] for r in range(nrhs)], axis=1)
+        U = np.stack([jacobi_pcg(A, F[:, r], con, rtol=rtol)[0] for r in range(nrhs)], axis=1)
     ra = np.array([
         apparent_resistivity(axis, U[:, flat["pt_rhs"][i]], flat["pt_k"][i], flat["pt_z0"][i], flat["pt_z1"][i], flat["scale"])
         for i in range(flat["pt_rhs"].shape[0])
     ])
-    return {"space": space, "A": A, "constrained": con, "U": U, "ra": ra, "axis": axis}
+    return {"space": space, "A": A, "constrained": con, "U": U, "ra": ra, "axis": axis, "iters": iters}

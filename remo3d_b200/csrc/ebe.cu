@@ -568,7 +568,7 @@ void ebe_build(Ctx* c) {
   int* umax_d = scratch<int>(c, 6, 1);
   CK(cudaMemsetAsync(umax_d, 0, sizeof(int), st));
   SpaceView sview = make_view(c);
-  static const int color = [] { const char* e = getenv("REMO_EBE_COLOR"); return e ? atoi(e) : 1; }();
+  static const int color = [] { const char* e = getenv("REMO_EBE_COLOR"); return e ? atoi(e) : 0; }();  // off until the greedy build is cheap (53 ms at 4.8 M dofs for 0.05 ms per product)
   LAUNCH(c, k_ebe_batch<false>, (unsigned)nb, TPB, 0, sview, tperm, split, color, c->constrained.p, ucount, umax_d, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
   LAUNCH(c, k_ebe_offsets_in, grid_for(nb + 1, TPB), TPB, 0, ucount, nb, uin);
   c->ebe_uoff.ensure(nb + 1, st);

@@ -145,7 +145,7 @@ def test_preconditioner_pieces_come_from_the_elements(ctx, dim, order):
     A = fo.assemble(mesh.points, space, sigma, mesh.mat)
     con = space.dirichlet_dofs(mesh.bfacets, flags)
     want = np.where(con, 0.0, 1.0 / A.diagonal())
-    np.testing.assert_allclose(dinv, want, rtol=1e-13, atol=0)
+    np.testing.assert_allclose(dinv, want, rtol=1e-11, atol=0)  # vs the oracle; bit-identical to the library's own CSR below
     Avv = A[: mesh.nv][:, : mesh.nv].tocsr()
     Avv.sort_indices()
     np.testing.assert_array_equal(rp, Avv.indptr)
