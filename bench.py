@@ -289,9 +289,46 @@ def run_b200(args):
     if os.environ.get("REMO_BENCH_DEBUG"):
         log("debug: dev %.1f ms, e2e %.1f ms, profiled (no graph) %.1f ms" % (ms_dev, ms_e2e, ms_prof))
     clocks = sampler.stop() if sampler else None
+    # everything that describes the main workload is read BEFORE the companion legs below load other meshes
+    ndof, nnz = ctx.ndof, ctx.nnz  # nnz: builds the CSR pattern now, outside the timed regions (the PCG path never needs it)
+    amg_levels = ctx.precond_get()[2] if args.preconditioner == "multigrid" else []
+    try:
+        asm_ms = float(ctx.kernel_time(1, nrhs, 3))
+    except Exception as exc:  # reporting only
+        asm_ms = None
+        log("assembly timing failed: %r" % exc)
+    main_info = dict(info)
+
+    def companion(mesh, steps):
+        """The same timed loop on another mesh of the same generator (all contexts, device-resident arrays)."""
+        _, d2 = load(mesh)
+        for i in range(nctx):
+            step(d2, i)
+        ms = timed(d2, steps)
+        return {"value": npts * steps * world / (ms / 1e3), "ms_per_step": ms / steps, "iterations": info.get("iters"), "max_relres": info.get("relres"),
+                "ndof": ctxs[0].ndof, "steps": steps}, ra_hosts[0].numpy().copy()
+
+    plain, like = None, None
+    if world == 1 and not args.no_companions:
+        if mesh_rounds() > 0:
+            # like-for-like with round 1's first sessions: the same workload on the mesh WITHOUT the sliver pass
+            saved = os.environ.get("REMO_BENCH_MESH_IMPROVE")
+            os.environ["REMO_BENCH_MESH_IMPROVE"] = "0"
+            try:
+                plain, _ = companion(make_mesh(args.size, task, log), args.steps)
+            except Exception as exc:
+                log("plain-mesh leg failed: %r" % exc)
+            finally:
+                if saved is None:
+                    os.environ.pop("REMO_BENCH_MESH_IMPROVE", None)
+                else:
+                    os.environ["REMO_BENCH_MESH_IMPROVE"] = saved
+        if not args.no_cpu_baseline:
+            # the CPU arm's larger sample through the GPU arm: both sides of `like_for_like` are measured on one mesh, and
+            # the apparent resistivities of the two arms are compared (parity on the benchmarked generator)
+            like, like_ra = companion(make_mesh(args.cpu_size2, task, log), max(8, args.steps))
 
     if rank == 0:
-        ndof, nnz = ctx.ndof, ctx.nnz
         total_pts = npts * args.steps * world
         value = total_pts / (ms_dev / 1e3)
         e2e = total_pts / (ms_e2e / 1e3)
@@ -303,12 +340,14 @@ def run_b200(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         per_launch = spmm_ms / max(spmm_n, 1) / 1e3
         traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per SpMM launch from the committed ncu --set full capture
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_spmm%s_traffic_%s.json" % ("_ebe" if kind == 2 else "", args.size))))
-            if tj.get("order") == args.order and tj.get("nrhs") == nrhs and kind != 0:
-                traffic = tj["traffic_bytes_per_launch"]
-        except Exception:
-            pass
+        for rnd in ("r02", "r01"):  # the newest committed ncu --set full capture of this kernel at this size
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "%s_spmm%s_traffic_%s.json" % (rnd, "_ebe" if kind == 2 else "", args.size))))
+                if tj.get("order") == args.order and tj.get("nrhs") == nrhs and kind != 0:
+                    traffic = tj["traffic_bytes_per_launch"]
+                    break
+            except Exception:
+                pass
         achieved = spmm_bytes(nnz, ndof, nrhs) / per_launch / 1e9 if spmm_n else 0.0
         h2d = sum(host[k].numel() * host[k].element_size() for k in names) + flat["src_z"].nbytes * 2 + flat["src_ptr"].nbytes \
             + flat["pt_rhs"].nbytes + 3 * flat["pt_z0"].nbytes + len(SIGMA) * 8
@@ -321,13 +360,14 @@ def run_b200(args):
                             "order-%d H1, one mesh task per step (batch_size 5, 4 tools), size %s" % (args.order, args.size),
                 "ndof": ndof, "nnz": nnz, "nnz_per_row": nnz / ndof, "vertices": int(m["points"].shape[0]), "tets": int(m["elems"].shape[0]),
                 "nrhs": nrhs, "points_per_step": npts, "solves_per_step": nrhs, "preconditioner": args.preconditioner,
-                "rtol": 1e-10, "iterations": info.get("iters"), "max_relres": info.get("relres"),
+                "rtol": 1e-10, "iterations": main_info.get("iters"), "max_relres": main_info.get("relres"),
                 "l2": "inputs larger than L2 (matrix %.0f MB + vectors %.0f MB vs 126 MB L2); no explicit flush" % (12e-6 * nnz, 48e-6 * ndof * nrhs),
                 "sharding": "independent mesh tasks per rank, no data-path collective",
                 "contexts_per_gpu": nctx, "stage_ms_one_context_alone": stage,
                 "mesh_sliver_pass_rounds": mesh_rounds(),
                 "options": {k: float(v) for k, v in bench_opts},
-                "amg_levels": ctx.precond_get()[2] if args.preconditioner == "multigrid" else [],
+                "amg_levels": amg_levels,
+                "value_plain_mesh": plain,
             },
             "e2e": {"value": e2e, "unit": "log points/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(npts * 8),
                     "ms_per_step": ms_e2e / args.steps},
@@ -337,6 +377,11 @@ def run_b200(args):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "bytes_per_launch": spmm_bytes(nnz, ndof, nrhs), "avg_launch_ms": per_launch * 1e3, "launches_timed": int(spmm_n),
                          "frac_of_8TBs_spec": achieved / 8000.0, "spmm_share_of_step": spmm_ms / ms_prof,
+                         "bytes_note": "achieved / frac use the ALGORITHMIC bytes of the CSR SpMM this launch replaces (SURVEY 8d: 12 nnz + N (8 + 16 k)); "
+                                       "the element-wise kernel (kind 2) reads no matrix and really moves `traffic` bytes",
+                         "frac_of_measured_traffic": (traffic / per_launch / 1e9 / peak) if (traffic and spmm_n) else None,
+                         "limiter": ("shared-memory / L1 data pipe (ncu: l1tex throughput ~87 %, DRAM ~25-40 %): bound=hbm names the roofline the "
+                                     "contract asks for, not the unit that saturates") if kind == 2 else "latency x concurrency of the scattered P-row gathers",
                          "timed_with": "CUDA events around every SpMM launch in %d extra steps run right after the timed regions (plain launches instead of the CUDA graph)" % args.steps},
         }
         try:
@@ -345,7 +390,7 @@ def run_b200(args):
             # map (4 B) and values (8 B)
             ldof = {1: 4, 2: 10, 3: 20}[args.order]
             abytes = float(m["elems"].shape[0]) * (16 + 96 + 4 + 12 * ldof * ldof)
-            ams = float(ctx.kernel_time(1, nrhs, 3))
+            ams = asm_ms
             line["assembly"] = {"ms": ams, "algorithmic_bytes": abytes, "achieved": abytes / ams / 1e6, "unit": "GB/s",
                                 "frac": abytes / ams / 1e6 / peak, "nnz_per_s": nnz / ams * 1e3,
                                 "note": "element metrics + atomic-free row-gather assembly of the whole CSR matrix (remo_kernel_time, CUDA events, "
@@ -354,7 +399,21 @@ def run_b200(args):
         except Exception as e:  # reporting only
             line["assembly"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args, log)
+            cb = cpu_baseline(args, log)
+            ra_cpu = np.asarray(cb.pop("_ra_sample"))
+            line["cpu_baseline"] = cb
+            if like is not None:
+                err = float(np.max(np.abs(like_ra - ra_cpu) / np.abs(ra_cpu)))
+                line["parity"] = {"max_rel_err_ra": err, "n_points": int(ra_cpu.shape[0]), "tol": 1e-6, "ndof": like["ndof"],
+                                  "what": "apparent resistivities of one C4 mesh task (size %s, sliver pass %d) from the GPU arm vs the CPU arm "
+                                          "(oracle, two-level PCG), both to relative residual 1e-10" % (args.cpu_size2, mesh_rounds())}
+                line["like_for_like"] = {"ndof": like["ndof"], "gpu_value": like["value"], "gpu_ms_per_step": like["ms_per_step"],
+                                         "gpu_iterations": like["iterations"], "cpu_value": cb["sample_value_unscaled"],
+                                         "cpu_iterations": cb["sample_iterations"], "ratio": like["value"] / cb["sample_value_unscaled"],
+                                         "unit": "log points/s", "note": "both arms MEASURED on the same mesh (no extrapolation)"}
+                if not err <= 1e-6:
+                    emit(line)
+                    raise SystemExit("bench.py: GPU and CPU arms disagree on the apparent resistivities: max rel err %.3e > 1e-6" % err)
         emit(line)
     if world > 1:
         dist.barrier()
@@ -366,6 +425,9 @@ def run_b200(args):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (NumPy/SciPy restatement of the reference path) farmed over the host cores
 # ------------------------------------------------------------------------------------------------
+CPU_RTOL = 1e-10  # the same stopping criterion as the GPU arm
+
+
 def _cpu_task(payload):
     from threadpoolctl import threadpool_limits
 
@@ -374,8 +436,11 @@ def _cpu_task(payload):
     threadpool_limits(1)  # one BLAS/OpenMP thread per worker process: the farm supplies the parallelism
     m, flat, order = payload
     t0 = time.time()
-    res = fo.solve_task(m["points"], m["elems"], m["mat"], SIGMA, m["bfacets"], m["bdir"].astype(bool), order, flat, solver="pcg")
-    return time.time() - t0, res["ra"].tolist(), res["space"].ndof
+    # solver="multigrid": the reference's default preconditioner (remo3d.py:82 -> ngsolve_functions.py:46), restated as
+    # exact sparse LU of the P1 block + Jacobi on the high-order dofs, all right-hand sides of the task in one block
+    res = fo.solve_task(m["points"], m["elems"], m["mat"], SIGMA, m["bfacets"], m["bdir"].astype(bool), order, flat, solver="multigrid",
+                        rtol=CPU_RTOL)
+    return time.time() - t0, res["ra"].tolist(), res["space"].ndof, [int(i) for i in res["iters"]]
 
 
 def cpu_farm(size, order, steps, workers):
@@ -386,31 +451,36 @@ def cpu_farm(size, order, steps, workers):
     m = make_mesh(size, task)
     npts = flat["pt_rhs"].shape[0]
     ctxm = mp.get_context("fork")
+    rounds = []
     with ctxm.Pool(workers) as pool:
         t0 = time.time()
-        ndof = 0
         for _ in range(steps):
+            t1 = time.time()
             out = pool.map(_cpu_task, [(m, flat, order)] * workers)
-            ndof = out[0][2]
+            rounds.append(time.time() - t1)
         wall = time.time() - t0
-    return {"value": npts * workers * steps / wall, "wall_s": wall, "ndof": ndof, "points": npts * workers * steps,
-            "round_s": wall / steps}
+    return {"value": npts * workers * steps / wall, "wall_s": wall, "ndof": out[0][2], "points": npts * workers * steps,
+            "round_s": float(np.median(rounds)), "rounds_s": rounds, "ra": out[0][1], "iters": out[0][3], "size": size}
 
 
 def cpu_scaled(args, rounds, log):
-    """CPU arm on BOUNDED samples of workload C4, scaled to the full workload.
+    """CPU arm on BOUNDED samples of workload C4.
 
-    The oracle cannot finish a ~5 M-dof task in minutes, so the farm is timed on the same generator at two reduced sizes
-    (same order, same 5 right-hand sides, same tolerance); the measured growth exponent p of the time per task,
-    t ~ ndof^p (assembly ~ N, Jacobi-PCG ~ N^(4/3) in 3D), extrapolates the round time to the dof count of `--size`.
-    value = log points of one round / extrapolated round time."""
+    The oracle cannot finish a ~5 M-dof task in minutes (SciPy assembly of 137 M non-zeros + a sparse LU of the 613 k-row
+    P1 block per worker process), so the farm is MEASURED on the same generator at two reduced sizes (same order, same 5
+    right-hand sides, same tolerance, the reference's default two-level preconditioner).  Two numbers come out:
+      * `like_for_like`: the larger sample (--cpu-size2, ~202 k dofs) is also run through the GPU arm by run_b200, so both
+        sides of that ratio are measurements on the same mesh;
+      * `value`: the round time extrapolated to the dof count of `--size` with the growth exponent p MEASURED between
+        the two samples (t ~ ndof^p; clamped to [1.2, 1.8]: the sparse LU of the P1 block and the iteration count both
+        grow faster than linearly in 3D)."""
     workers = os.cpu_count() or 1
     task, flat = make_task()
     npts = flat["pt_rhs"].shape[0]
-    small = cpu_farm(args.cpu_size, args.order, rounds, workers)
-    big = cpu_farm(args.cpu_size2, args.order, 1, workers)
-    p = float(np.log(big["round_s"] / small["round_s"]) / np.log(big["ndof"] / small["ndof"]))
-    p = min(max(p, 1.0), 2.0)
+    small = cpu_farm(args.cpu_size, args.order, 1, workers)
+    big = cpu_farm(args.cpu_size2, args.order, max(2, rounds), workers)
+    p_raw = float(np.log(big["round_s"] / small["round_s"]) / np.log(big["ndof"] / small["ndof"]))
+    p = min(max(p_raw, 1.2), 1.8)
     full = FULL_DOFS.get((args.size, args.order))
     if full is None:  # dof count of the GPU arm's mesh: vertices + edges (order 2), counted from the cached mesh
         from oracle import fem_oracle as fo
@@ -421,23 +491,27 @@ def cpu_scaled(args, rounds, log):
         full = big["ndof"]
     t_full = big["round_s"] * (full / big["ndof"]) ** p
     value = npts * workers / t_full
-    log("cpu arm: %d workers; %s: %d dofs %.1f s/round; %s: %d dofs %.1f s/round; exponent %.2f -> %.0f s/round at %d dofs" % (
-        workers, args.cpu_size, small["ndof"], small["round_s"], args.cpu_size2, big["ndof"], big["round_s"], p, t_full, full))
-    sample = ("oracle/fem_oracle.py (NumPy/SciPy restatement of the reference path, Jacobi-PCG; NGSolve is not installable) farmed over %d "
-              "worker processes on bounded samples of workload C4: size %s (%d dofs) %.1f s per round x %d rounds, size %s (%d dofs) %.1f s per "
-              "round; time per task ~ ndof^%.2f (measured) extrapolated to %d dofs -> %.0f s per round of %d tasks; unscaled sample "
-              "throughput %.2f log points/s" % (workers, args.cpu_size, small["ndof"], small["round_s"], rounds, args.cpu_size2, big["ndof"],
-                                                big["round_s"], p, full, t_full, workers, small["value"]))
+    log("cpu arm: %d workers; %s: %d dofs %.1f s/round; %s: %d dofs %s s/round (iterations %s); exponent %.2f (raw %.2f) -> %.0f s/round at %d dofs" % (
+        workers, args.cpu_size, small["ndof"], small["round_s"], args.cpu_size2, big["ndof"], ["%.1f" % r for r in big["rounds_s"]], big["iters"],
+        p, p_raw, t_full, full))
+    sample = ("oracle/fem_oracle.py (NumPy/SciPy restatement of the reference path with its default preconditioner: exact sparse LU of the P1 "
+              "block + Jacobi on the high-order dofs, PCG to 1e-10, 5 right-hand sides per task in one block; NGSolve is not installable) farmed "
+              "over %d worker processes on bounded samples of workload C4: size %s (%d dofs) %.1f s per round, size %s (%d dofs) median %.1f s "
+              "per round of %d rounds (%s iterations); time per task ~ ndof^%.2f (measured %.2f, clamped to [1.2, 1.8]) extrapolated to %d dofs "
+              "-> %.0f s per round of %d tasks; MEASURED throughput on the %s sample: %.2f log points/s"
+              % (workers, args.cpu_size, small["ndof"], small["round_s"], args.cpu_size2, big["ndof"], big["round_s"], len(big["rounds_s"]),
+                 big["iters"], p, p_raw, full, t_full, workers, args.cpu_size2, npts * workers / big["round_s"]))
     return {"value": value, "unit": "log points/s", "cores": workers, "kind": "port", "sample": sample,
-            "sample_value_unscaled": small["value"], "exponent": p, "wall_s": small["wall_s"] + big["wall_s"],
-            "round_points": npts * workers}
+            "sample_value_unscaled": npts * workers / big["round_s"], "sample_ndof": big["ndof"], "sample_size": args.cpu_size2,
+            "sample_iterations": big["iters"], "exponent": p, "exponent_measured": p_raw,
+            "wall_s": small["wall_s"] + big["wall_s"], "round_points": npts * workers, "_ra_sample": big["ra"]}
 
 
-FULL_DOFS = {("5M", 2): 4820927, ("1M", 2): 1421970}
+FULL_DOFS = {("5M", 2): 4821007, ("1M", 2): 1422109}
 
 
 def cpu_baseline(args, log):
-    return cpu_scaled(args, 1, log)
+    return cpu_scaled(args, 2, log)
 
 
 def run_reference(args):
@@ -451,7 +525,8 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["round_points"] / r["value"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C4 (same generator, order %d), CPU arm on bounded samples scaled to size %s" % (args.order, args.size)},
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "sample_value_unscaled", "sample_ndof", "exponent",
+                                               "exponent_measured")},
             "e2e": {"value": r["value"], "unit": "log points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -488,6 +563,7 @@ def main():
     ap.add_argument("--preconditioner", default="multigrid", choices=["local", "multigrid"])
     ap.add_argument("--maxit", type=int, default=20000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-companions", action="store_true", help="skip the plain-mesh and like-for-like GPU legs (N = 1 only)")
     ap.add_argument("--contexts", type=int, default=2, help="solver contexts (stream + host thread) per GPU")
     args = ap.parse_args()
     if args.impl == "reference":

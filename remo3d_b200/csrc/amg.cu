@@ -21,6 +21,7 @@
 //     (always a contraction), symmetric cycle, coarse correction over-weighted by 1.5 (plain aggregation
 //     under-corrects) -> M is SPD and plain PCG applies.
 // Everything works on row-major n x nrhs blocks, like the PCG.
+#include <cooperative_groups.h>
 #include <cub/cub.cuh>
 
 #include <cstdlib>
@@ -32,7 +33,7 @@ namespace {
 
 constexpr int TB = 256;
 constexpr int AGG = 8;
-constexpr int COARSEST = 256;
+constexpr int COARSEST = 64;  // dense inverse below this: Gauss-Jordan by one CTA costs ~n^3 / 1024 global updates (9 ms at n = 250)
 constexpr int MAXLEV = 12;
 
 double env_d(const char* name, double def) {
@@ -186,9 +187,9 @@ __global__ void k_morton(const double* __restrict__ xyz, int64_t nv, int dim, co
 }
 
 // perm = vertices in Morton order -> aggregate of vertex perm[p] is p / AGG  (amg_agg = 0: the round-1 aggregates)
-__global__ void k_agg_from_perm(const uint32_t* __restrict__ perm, int64_t n, int32_t* __restrict__ agg) {
+__global__ void k_agg_from_perm(const uint32_t* __restrict__ perm, const double* __restrict__ diag, int64_t n, int32_t* __restrict__ agg) {
   int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (p < n) agg[perm[p]] = (int32_t)(p / AGG);
+  if (p < n) agg[perm[p]] = diag[perm[p]] > 0.0 ? (int32_t)(p / AGG) : -1;  // constrained vertices join no aggregate
 }
 __global__ void k_agg_consecutive(int64_t n, int32_t* __restrict__ agg) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -367,6 +368,146 @@ __global__ void k_dense_apply(int n, const double* __restrict__ Ainv, const doub
   if (ok && part == 0) X[e] = s;
 }
 
+// ---------------------------------------------------------------- the small levels of the V-cycle in ONE launch
+// Below ~16 k rows a level's kernels are pure launch latency (5 launches of 3-10 us per level and V-cycle, ~25 launches
+// = ~120 us of a 1.3 ms PCG iteration at 4.8 M dofs).  k_vcycle_tail runs the whole sub-cycle of those levels -- first
+// sweep, residual, restriction down to the dense coarsest solve, then prolongation and smoothing back up -- as one
+// thread-block CLUSTER of 8 CTAs x 1024 threads: the phases are separated by the hardware cluster barrier
+// (barrier.cluster arrive.release / wait.acquire orders the global-memory traffic between the CTAs), the data stays in
+// L2.  Same arithmetic as the per-level kernels (k_jacobi0, k_smooth, k_restrict, k_prolong, k_dense_apply), and for the
+// strides 6 and 8 (5..8 right-hand sides: k_smooth<4,4,2>) also the same summation order, i.e. bit-identical results
+// (remo_set_option("amg_fused_tail", 0) selects the per-level launches).  Column pairs: ks even, ks <= 8.
+struct TailLevel {
+  const int64_t* rowptr;
+  const int32_t* col;
+  const double* val;
+  const double* dinv;
+  const int32_t* agg;
+  const int32_t* aggptr;
+  const int32_t* members;
+  const double* b;
+  double* x;
+  double* t;
+  int64_t n;
+  double omega;
+};
+struct TailArgs {
+  TailLevel L[MAXLEV];
+  int nl;               // levels handled here; the last one is the coarsest (dense inverse)
+  const double* dense;  // inverse of the coarsest matrix
+  int k;                // row stride of the blocks (even, <= 8)
+  int sweeps;
+  double alpha;
+};
+constexpr int TAIL_CTAS = 8, TAIL_THREADS = 1024;
+
+// OUT = X + omega dinv (B - A X) (mode 0) or B - A X (mode 1): the loop of k_smooth<4, 4, 2> over the cluster's threads
+__device__ __forceinline__ void tail_smooth(const TailLevel& L, const double* __restrict__ X, double* __restrict__ OUT, int ks, int mode,
+                                            int ctid, int nthreads) {
+  constexpr int G = 4;
+  const int lane = ctid & 31;
+  const int gl = ctid % G;
+  const int r2 = gl;
+  const bool on = 2 * r2 < ks;
+  const int cc = on ? 2 * r2 : 0;
+  const unsigned gmask = ((1u << G) - 1u) << ((lane / G) * G);
+  for (int64_t row = ctid / G; row < L.n; row += nthreads / G) {
+    const int64_t s = L.rowptr[row], e = L.rowptr[row + 1];
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int64_t base = s; base < e; base += G) {
+      int32_t myc = (int32_t)row;
+      double myv = 0.0;
+      if (base + gl < e) { myc = L.col[base + gl]; myv = L.val[base + gl]; }
+#pragma unroll
+      for (int i = 0; i < G; i++) {
+        const int32_t c = __shfl_sync(gmask, myc, i, G);
+        const double v = __shfl_sync(gmask, myv, i, G);
+        const double2 x = *reinterpret_cast<const double2*>(X + (int64_t)c * ks + cc);
+        acc0 = fma(v, x.x, acc0);
+        acc1 = fma(v, x.y, acc1);
+      }
+    }
+    if (on) {
+      const int64_t idx = row * ks + cc;
+      const double w = L.omega * L.dinv[row];
+      const double res0 = L.b[idx] - acc0, res1 = L.b[idx + 1] - acc1;
+      OUT[idx] = (mode == 1) ? res0 : fma(w, res0, X[idx]);
+      OUT[idx + 1] = (mode == 1) ? res1 : fma(w, res1, X[idx + 1]);
+    }
+  }
+}
+
+__global__ void __cluster_dims__(TAIL_CTAS, 1, 1) __launch_bounds__(TAIL_THREADS) k_vcycle_tail(const __grid_constant__ TailArgs a) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int ctid = (int)cluster.block_rank() * TAIL_THREADS + threadIdx.x;
+  const int nthreads = TAIL_CTAS * TAIL_THREADS;
+  const int k = a.k, nl = a.nl;
+  double* xs[MAXLEV];
+  double* ts[MAXLEV];
+#pragma unroll
+  for (int l = 0; l < MAXLEV; l++) { xs[l] = a.L[l].x; ts[l] = a.L[l].t; }
+  // ---- down
+  for (int l = 0; l < nl - 1; l++) {
+    const TailLevel& L = a.L[l];
+    for (int64_t e = ctid; e < L.n * k; e += nthreads) xs[l][e] = L.omega * L.dinv[e / k] * L.b[e];
+    cluster.sync();
+    for (int sw = 1; sw < a.sweeps; sw++) {
+      tail_smooth(L, xs[l], ts[l], k, 0, ctid, nthreads);
+      double* tmp = xs[l]; xs[l] = ts[l]; ts[l] = tmp;
+      cluster.sync();
+    }
+    tail_smooth(L, xs[l], ts[l], k, 1, ctid, nthreads);  // t = b - A x
+    cluster.sync();
+    const TailLevel& C = a.L[l + 1];
+    double* bc = const_cast<double*>(C.b);
+    for (int64_t e = ctid; e < C.n * k; e += nthreads) {
+      const int64_t ag = e / k;
+      const int r = (int)(e - ag * k);
+      double sum = 0.0;
+      for (int32_t p = L.aggptr[ag]; p < L.aggptr[ag + 1]; p++) sum += ts[l][(int64_t)L.members[p] * k + r];
+      bc[e] = sum;
+    }
+    cluster.sync();
+  }
+  // ---- coarsest: x = Ainv b, 8 lanes per entry as k_dense_apply
+  {
+    const TailLevel& L = a.L[nl - 1];
+    const int n = (int)L.n;
+    for (int base = 0; base < n * k * 8; base += nthreads) {
+      const int t = base + ctid;
+      const int e = t >> 3, part = t & 7;
+      double sum = 0.0;
+      const bool ok = e < n * k;
+      const int i = ok ? e / k : 0, r = ok ? e - i * k : 0;
+      if (ok)
+        for (int j = part; j < n; j += 8) sum = fma(a.dense[(int64_t)i * n + j], L.b[(int64_t)j * k + r], sum);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      if (ok && part == 0) xs[nl - 1][e] = sum;
+    }
+    cluster.sync();
+  }
+  // ---- up
+  for (int l = nl - 2; l >= 0; l--) {
+    const TailLevel& L = a.L[l];
+    const double* xc = xs[l + 1];
+    for (int64_t e = ctid; e < L.n * k; e += nthreads) {
+      const int64_t i = e / k;
+      const int r = (int)(e - i * k);
+      const int32_t ag = L.agg[i];
+      if (ag >= 0 && L.dinv[i] != 0.0) xs[l][e] = fma(a.alpha, xc[(int64_t)ag * k + r], xs[l][e]);
+    }
+    cluster.sync();
+    for (int sw = 0; sw < a.sweeps; sw++) {
+      tail_smooth(L, xs[l], ts[l], k, 0, ctid, nthreads);
+      double* tmp = xs[l]; xs[l] = ts[l]; ts[l] = tmp;
+      cluster.sync();
+    }
+  }
+}
+
 int kp_of(int k) {
   int kp = 1;
   while (kp < k) kp <<= 1;
@@ -496,8 +637,9 @@ int64_t aggregate_pairwise(Ctx* c, Ctx::AmgLevel& F, Ctx::AmgLevel& C) {
     }
     LAUNCH(c, k_pair_flags, grid_for(n, TB), TB, 0, match, n, flag);
     nc = inclusive_scan_total(c, flag, incl, n);
-    if (nc > (int64_t)(0.8 * (double)n) && n > COARSEST) {
-      // the strength graph hardly matched anything (no negative couplings left): pairs of consecutive live rows
+    if (nc > (int64_t)(0.7 * (double)n) && n > COARSEST) {
+      // the strength graph hardly matched anything (small coarse levels are nearly dense, with few negative couplings
+      // left): pairs of consecutive live rows instead -- the numbering keeps the locality of the level above
       LAUNCH(c, k_live_flags, grid_for(n, TB), TB, 0, cur.diag, n, flag);
       const int64_t live = inclusive_scan_total(c, flag, incl, n);
       nc = (live + 1) / 2;
@@ -554,7 +696,7 @@ void amg_build_hierarchy(Ctx* c) {
         c->tmp.ensure(bytes, st);
         CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, code, codes, idx, perm, F.n, 0, 63, st));
         c->launches += 4;
-        LAUNCH(c, k_agg_from_perm, grid_for(F.n, TB), TB, 0, perm, F.n, F.agg.p);
+        LAUNCH(c, k_agg_from_perm, grid_for(F.n, TB), TB, 0, perm, F.diag.p, F.n, F.agg.p);
       } else {
         LAUNCH(c, k_agg_consecutive, grid_for(F.n, TB), TB, 0, F.n, F.agg.p);
       }
@@ -630,8 +772,15 @@ void amg_apply(Ctx* c, const double* R, double* Z, int k) {
   const int sweeps = c->amg_sweeps;
   const int nl = c->amg_nlev;
   amg_prepare(c, k);
-  // down
-  for (int l = 0; l < nl - 1; l++) {
+  // levels [lt, nl) go into the fused tail kernel: every level below TAIL_ROWS rows, but never level 0 (its right-hand
+  // side / result are the PCG's blocks) and only for column-pair strides the kernel is written for
+  int lt = nl;
+  if (c->amg_fused_tail && (k & 1) == 0 && k <= 8 && nl >= 2) {
+    lt = nl - 1;
+    while (lt > 1 && c->amg[lt - 1].n <= c->amg_tail_rows) lt--;
+    if (nl - lt < 2) lt = nl;  // the coarsest level alone: nothing to fuse
+  }
+  auto down = [&](int l) {
     Ctx::AmgLevel& L = c->amg[l];
     const double* b = (l == 0) ? R : L.b.p;
     const double omega = L.omega;
@@ -643,15 +792,8 @@ void amg_apply(Ctx* c, const double* R, double* Z, int k) {
     spmm_smooth(c, L.rowptr.p, L.col.p, L.val.p, L.dinv.p, b, L.x.p, L.t.p, k, L.n, omega, 1);  // t = b - A x
     Ctx::AmgLevel& C = c->amg[l + 1];
     LAUNCH(c, k_restrict, grid_for(C.n * k, TB), TB, 0, L.aggptr.p, L.members.p, L.t.p, C.b.p, k, C.n);
-  }
-  {  // coarsest: dense inverse
-    Ctx::AmgLevel& L = c->amg[nl - 1];
-    const double* b = (nl == 1) ? R : L.b.p;
-    double* x = (nl == 1) ? Z : L.x.p;
-    LAUNCH(c, k_dense_apply, grid_for(L.n * k * 8, 128), 128, 0, (int)L.n, c->amg_dense.p, b, x, k);
-  }
-  // up
-  for (int l = nl - 2; l >= 0; l--) {
+  };
+  auto up = [&](int l) {
     Ctx::AmgLevel& L = c->amg[l];
     Ctx::AmgLevel& C = c->amg[l + 1];
     const double* b = (l == 0) ? R : L.b.p;
@@ -662,6 +804,37 @@ void amg_apply(Ctx* c, const double* R, double* Z, int k) {
       spmm_smooth(c, L.rowptr.p, L.col.p, L.val.p, L.dinv.p, b, L.x.p, out, k, L.n, omega, 0);
       if (out == L.t.p) std::swap(L.x.p, L.t.p);
     }
+  };
+  const int top = std::min(lt, nl - 1);  // per-level launches for the levels [0, top)
+  for (int l = 0; l < top; l++) down(l);
+  if (lt < nl) {
+    TailArgs a;
+    memset(&a, 0, sizeof a);
+    a.nl = nl - lt;
+    a.dense = c->amg_dense.p;
+    a.k = k;
+    a.sweeps = sweeps;
+    a.alpha = alpha;
+    for (int l = lt; l < nl; l++) {
+      Ctx::AmgLevel& L = c->amg[l];
+      TailLevel& T = a.L[l - lt];
+      T.rowptr = L.rowptr.p; T.col = L.col.p; T.val = L.val.p; T.dinv = L.dinv.p;
+      T.agg = L.agg.p; T.aggptr = L.aggptr.p; T.members = L.members.p;
+      T.b = L.b.p; T.x = L.x.p; T.t = L.t.p; T.n = L.n; T.omega = L.omega;
+    }
+    k_vcycle_tail<<<TAIL_CTAS, TAIL_THREADS, 0, st>>>(a);
+    c->launches++;
+    CK(cudaGetLastError());
+    // mirror the kernel's pointer swaps: the result of a non-coarsest tail level ends up where its t block was after an
+    // odd number of swaps
+    for (int l = lt; l < nl - 1; l++)
+      if (((sweeps - 1) + sweeps) & 1) std::swap(c->amg[l].x.p, c->amg[l].t.p);
+  } else {  // coarsest: dense inverse
+    Ctx::AmgLevel& L = c->amg[nl - 1];
+    const double* b = (nl == 1) ? R : L.b.p;
+    double* x = (nl == 1) ? Z : L.x.p;
+    LAUNCH(c, k_dense_apply, grid_for(L.n * k * 8, 128), 128, 0, (int)L.n, c->amg_dense.p, b, x, k);
   }
+  for (int l = top - 1; l >= 0; l--) up(l);
   // the high-order rows (z = D^-1 r) are handled inside the PCG vector kernels (k_init / k_update_r / k_update_px, tail_from = nv)
 }

@@ -409,6 +409,8 @@ int remo_set_option(void* vctx, const char* name, double value) {
     else if (n == "amg_passes") { c->amg_passes = std::min(8, std::max(1, (int)value)); c->pkind = -1; }
     else if (n == "amg_rounds") { c->amg_rounds = std::min(32, std::max(1, (int)value)); c->pkind = -1; }
     else if (n == "lazy_matrix") c->lazy_matrix = value != 0.0;
+    else if (n == "amg_fused_tail") c->amg_fused_tail = value != 0.0 ? 1 : 0;
+    else if (n == "amg_tail_rows") c->amg_tail_rows = (int64_t)value;
     else FAIL(REMO_ERR_ARG, "remo_set_option: unknown option '%s'", name);
     return REMO_OK;
   });

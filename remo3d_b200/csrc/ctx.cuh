@@ -164,6 +164,8 @@ struct Ctx {
   int amg_agg = 1;           // 1 = strength-based pairwise aggregation, 0 = Morton-rank aggregates of 8 (round 1)
   int amg_passes = 3;        // pairwise passes per level: aggregates of at most 2^passes rows
   int amg_rounds = 4;        // handshake rounds per pass
+  int amg_fused_tail = 1;    // the levels below amg_tail_rows rows run as one cluster kernel (amg.cu k_vcycle_tail)
+  int64_t amg_tail_rows = 20000;
   double amg_alpha = 1.5, amg_omega_scale = 1.0;  // coarse-correction scaling, weight of the l1-Jacobi sweeps (<= 1)
   int amg_sweeps = 1;                              // pre = post smoothing sweeps
   int amg_gamma = 1;                               // cycle index: 1 = V, 2 = W
@@ -222,11 +224,14 @@ static inline int allow_max_smem(K kern, int device) {
   CK(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   std::lock_guard<std::mutex> g(mu);
   const auto key = std::make_pair((const void*)kern, device);
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, kern));
+  const int room = dev_max - (int)fa.sharedSizeBytes;  // static + dynamic shared memory share the opt-in limit
   if (!done.count(key)) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_max));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, room));
     done.insert(key);
   }
-  return dev_max;
+  return room;
 }
 
 static inline unsigned grid_for(int64_t n, int block, int64_t cap = (1 << 30)) {

@@ -2,41 +2,81 @@
 
 The reference spawns MPI processes that each loop `mesh -> SolveBVP per source -> sample -> Ra`
 (`worker.py:74-138`).  Here a worker is a thread bound to one GPU context; a task (= one mesh and all the sources
-that share it, `remo3d.py:624-690`) is solved as ONE multi-right-hand-side system.  The failure contract is kept:
-any exception inside a task turns every log point of that task into NaN (`worker.py:135-138`); the message is kept
-in `errors` instead of being swallowed.
+that share it, `remo3d.py:624-690`) is solved as ONE multi-right-hand-side system (blocks of at most 32 right-hand
+sides: a task with more sources, `batch_size > 32`, is solved block after block on the same matrix).  The failure
+contract is kept: any exception inside a task -- mesh generation included, `worker.py:82-138` wraps both -- turns every
+log point of that task into NaN and the run goes on; the message is kept in the task record instead of being swallowed.
+A solve that stops at `maxit` is NOT a failure (NGSolve's `CGSolver(maxsteps=1000)` returns its last iterate too,
+`ngsolve_functions.py:50-51`): the values are kept and the record carries `noconv` with the residual reached.
 """
+import warnings
+
 import numpy as np
 
 from . import _cabi, planner
 
 DIRICHLET = "dirichlet_boundary"  # worker.py:90
+DEFAULT_MAXIT = {"multigrid": 1000, "local": 20000}  # ngsolve_functions.py:50 caps both at 1000; Jacobi needs ~2000 at 5 M dofs
 
 
-def solve_task(ctx, mesh, sigma, flat, order=3, preconditioner="multigrid", rtol=1e-10, maxit=1000):
+def rhs_blocks(flat, max_rhs=_cabi.MAX_RHS):
+    """Split the right-hand sides of a flattened task into blocks of at most `max_rhs`: yields (flat_block, point index)."""
+    nrhs = flat["src_ptr"].shape[0] - 1
+    if nrhs <= max_rhs:
+        yield flat, np.arange(flat["pt_rhs"].shape[0])
+        return
+    for lo in range(0, nrhs, max_rhs):
+        hi = min(nrhs, lo + max_rhs)
+        s0, s1 = int(flat["src_ptr"][lo]), int(flat["src_ptr"][hi])
+        sel = np.nonzero((flat["pt_rhs"] >= lo) & (flat["pt_rhs"] < hi))[0]
+        block = dict(flat)
+        block["src_ptr"] = flat["src_ptr"][lo:hi + 1] - s0
+        block["src_z"], block["src_fac"] = flat["src_z"][s0:s1], flat["src_fac"][s0:s1]
+        for k in ("pt_z0", "pt_z1", "pt_k", "pt_depth", "pt_tool"):
+            block[k] = flat[k][sel]
+        block["pt_rhs"] = (flat["pt_rhs"][sel] - lo).astype(np.int32)
+        yield block, sel
+
+
+def solve_task(ctx, mesh, sigma, flat, order=3, preconditioner="multigrid", rtol=1e-10, maxit=None):
     """One mesh task on one context -> (Ra per log point, per-task record).  Raises on failure."""
+    if maxit is None:
+        maxit = DEFAULT_MAXIT[preconditioner]
     ctx.mesh_set(mesh.dim, mesh.points, mesh.elems, mesh.mat, mesh.bfacets, mesh.dirichlet_flags(DIRICHLET), mesh.axis_vertices())
     ndof, _ = ctx.space_build(order)  # the CSR pattern (and its nnz) is built only on demand: not on this path
     ctx.assemble(np.asarray(sigma, dtype=np.float64))
     ctx.precond_setup(preconditioner)
-    ctx.rhs_point_sources(flat["src_ptr"], flat["src_z"], flat["src_fac"])
-    iters, relres = ctx.solve(rtol=rtol, maxit=maxit)
-    ra = ctx.apparent_resistivity(flat["pt_rhs"], flat["pt_z0"], flat["pt_z1"], flat["pt_k"], flat["scale"])
-    rec = {"ndof": ndof, "iters": iters.tolist(), "relres": float(relres.max())}
+    ra = np.empty(flat["pt_rhs"].shape[0])
+    iters, relres = [], []
+    for block, sel in rhs_blocks(flat):
+        ctx.rhs_point_sources(block["src_ptr"], block["src_z"], block["src_fac"])
+        it, rr = ctx.solve(rtol=rtol, maxit=maxit, raise_on_noconv=False)
+        ra[sel] = ctx.apparent_resistivity(block["pt_rhs"], block["pt_z0"], block["pt_z1"], block["pt_k"], block["scale"])
+        iters += it.tolist()
+        relres += rr.tolist()
+    rec = {"ndof": ndof, "iters": iters, "relres": float(max(relres))}
+    if rec["relres"] > rtol:
+        rec["noconv"] = "PCG stopped at maxit=%d with relative residual %.2e (> rtol %.1e): last iterate kept, like CGSolver(maxsteps)" % (
+            maxit, rec["relres"], rtol)
+        warnings.warn(rec["noconv"])
     rec.update(ctx.stage_times())
     return ra, rec
 
 
-def run_tasks(ctx, jobs, tools, order=3, preconditioner="multigrid", rtol=1e-10, maxit=1000):
-    """jobs: iterable of (task_index, task, mesh, sigma).  Yields (task_index, [[depth_idx, tool_idx, Ra], ...], record)."""
+def run_tasks(ctx, jobs, tools, order=3, preconditioner="multigrid", rtol=1e-10, maxit=None):
+    """jobs: iterable of (task_index, task, mesh, sigma) -- `mesh` may be an Exception raised by the mesh generator.
+    Yields (task_index, [[depth_idx, tool_idx, Ra], ...], record)."""
     for index, task, mesh, sigma in jobs:
-        flat = planner.flatten_task(task, tools, three_d=(mesh.dim == 3))
+        points = [(int(p[0]), int(p[1])) for st in task[2] for p in st[2]]  # worker.py:104-134: the task's log points
         try:
+            if isinstance(mesh, BaseException):
+                raise mesh
+            flat = planner.flatten_task(task, tools, three_d=(mesh.dim == 3))
             ra, rec = solve_task(ctx, mesh, sigma, flat, order, preconditioner, rtol, maxit)
+            triples = [[int(d), int(t), float(r)] for d, t, r in zip(flat["pt_depth"], flat["pt_tool"], ra)]
         except Exception as exc:  # NaN-on-failure contract of worker.py:135-138
-            ra = np.full(flat["pt_rhs"].shape[0], np.nan)
+            triples = [[d, t, float("nan")] for d, t in points]
             rec = {"error": "%s: %s" % (type(exc).__name__, exc)}
-        triples = [[int(d), int(t), float(r)] for d, t, r in zip(flat["pt_depth"], flat["pt_tool"], ra)]
         yield index, triples, rec
 
 
