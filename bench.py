@@ -514,6 +514,79 @@ def cpu_baseline(args, log):
     return cpu_scaled(args, 2, log)
 
 
+# ------------------------------------------------------------------------------------------------
+# pipeline mode: the whole measurement pipeline, host mesh generation inside the timed region
+# ------------------------------------------------------------------------------------------------
+def run_pipeline(args):
+    """`Model.simulate_logs` end to end: planner -> host mesh pool (one triangulation per electrode pattern,
+    materials per task) -> GPU workers -> gather, on the C5-shaped plan (--pipeline-depths depths x 4 tools, batch 5) of a
+    3-layer 10/100/10 ohm-m model dipping 30 degrees.  Everything is inside the timed region (wall clock: the host is part of
+    what is measured).  Under torchrun every rank drives its own GPU and every world-th task; one gather at the end."""
+    import torch
+    import torch.distributed as dist
+
+    from remo3d_b200 import Model
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; this arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    he, ha, g, hm = SIZES[args.pipeline_size]
+    formation = np.array([[-1000.0, 49.0, np.nan, np.nan, 10.0], [49.0, 51.5, np.nan, np.nan, 100.0], [51.5, 2000.0, np.nan, np.nan, 10.0]])
+    borehole = np.array([[-1000.0, 0.2, 1.0], [2000.0, 0.2, 1.0]])
+    depths = np.round(np.arange(args.pipeline_depths) * 0.1, 4)
+    model = Model(TOOLS)
+    model.set_model_parameters(formation, borehole, dip=30)
+    cpu = max(1, (os.cpu_count() or 1) // world)
+    model.initialize_workers(cpu_workers=cpu, gpu_workers=1, devices=[local], contexts_per_gpu=args.contexts)
+    opts = {"h_electrode": he, "h_axis": ha, "grading": g, "h_max": hm, "improve": mesh_rounds() if args.pipeline_improve else 0}
+    try:
+        # warm-up: one small call (CUDA context, kernels, pool processes), untimed
+        model.simulate_logs(depths[:2], order=args.order, preconditioner=args.preconditioner, mesh_options=dict(opts, h_electrode=0.1, h_axis=0.4, grading=0.6, improve=0))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        model.simulate_logs(depths, order=args.order, preconditioner=args.preconditioner, mesh_options=opts,
+                            task_shard=(rank, world) if world > 1 else None)
+        torch.cuda.synchronize()
+        wall = time.time() - t0
+    finally:
+        model.shutdown_workers()
+    st = model.pipeline_stats
+    if world > 1:
+        t = torch.tensor([wall, st["gpu_busy_fraction"], float(st["tasks"])], device="cuda", dtype=torch.float64)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        wall, busy, tasks = float(tmax[0]), float(t[1]) / world, int(t[2])
+    else:
+        busy, tasks = st["gpu_busy_fraction"], st["tasks"]
+    if rank == 0:
+        npts = sum(int(np.isfinite(model.logs[t][:, 1]).sum()) for t in TOOLS)
+        recs = [r for r in model.task_records if r and "error" not in r]
+        errs = [r for r in model.task_records if r and "error" in r]
+        line = {"metric": "log points/sec", "mode": "pipeline", "value": npts / wall, "unit": "log points/s", "n_gpus": world, "steps": 1, "warmup": 1,
+                "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "pipeline: Model.simulate_logs, %d depths x 4 tools, batch 5, 3 layers dipping 30 deg, half-ball R=50, order %d, "
+                                       "mesh size class %s; mesh generation inside the timed region" % (args.pipeline_depths, args.order, args.pipeline_size),
+                           "tasks": tasks, "log_points": npts, "failed_tasks": len(errs), "first_error": errs[0]["error"] if errs else None,
+                           "ndof_median": float(np.median([r["ndof"] for r in recs])) if recs else None,
+                           "iterations_median": float(np.median([max(r["iters"]) for r in recs])) if recs else None,
+                           "gpu_busy_fraction": busy, "host_material_s_rank0": st["host_material_s"], "shared_geometry": st["shared_geometry"],
+                           "cpu_workers_per_rank": cpu, "contexts_per_gpu": args.contexts, "mesh_sliver_pass_rounds": opts["improve"],
+                           "solve_ms_median": float(np.median([r["solve"] for r in recs])) if recs else None,
+                           "timing": "wall clock around simulate_logs (host work is part of the measurement), max over ranks"}}
+        emit(line)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -565,9 +638,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-companions", action="store_true", help="skip the plain-mesh and like-for-like GPU legs (N = 1 only)")
     ap.add_argument("--contexts", type=int, default=2, help="solver contexts (stream + host thread) per GPU")
+    ap.add_argument("--mode", default="step", choices=["step", "pipeline"])
+    ap.add_argument("--pipeline-depths", type=int, default=1000)
+    ap.add_argument("--pipeline-size", default="200k", choices=list(SIZES))
+    ap.add_argument("--pipeline-improve", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "pipeline":
+        run_pipeline(args)
     else:
         run_b200(args)
 

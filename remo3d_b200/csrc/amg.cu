@@ -33,7 +33,7 @@ namespace {
 
 constexpr int TB = 256;
 constexpr int AGG = 8;
-constexpr int COARSEST = 64;  // dense inverse below this: Gauss-Jordan by one CTA costs ~n^3 / 1024 global updates (9 ms at n = 250)
+constexpr int COARSEST = 512;  // dense inverse below this many rows (one launch per pivot step, k_gj_step)
 constexpr int MAXLEV = 12;
 
 double env_d(const char* name, double def) {
@@ -312,45 +312,30 @@ __global__ void k_prolong(const int32_t* __restrict__ agg, const double* __restr
 
 // ---------------------------------------------------------------- coarsest level: dense inverse
 __global__ void k_dense_fill(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
-                             int n, double* __restrict__ M) {  // M = [A | I], n x 2n
-  for (int e = threadIdx.x; e < n * 2 * n; e += blockDim.x) {
-    const int i = e / (2 * n), j = e - i * 2 * n;
-    M[e] = (j == n + i) ? 1.0 : 0.0;
+                             int n, double* __restrict__ M) {  // dense n x n copy of the coarsest matrix
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool diag = false;
+  for (int64_t j = rowptr[i]; j < rowptr[i + 1]; j++) {
+    M[(int64_t)i * n + col[j]] = val[j];
+    if (col[j] == i && val[j] > 0.0) diag = true;
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    bool diag = false;
-    for (int64_t j = rowptr[i]; j < rowptr[i + 1]; j++) {
-      M[(int64_t)i * 2 * n + col[j]] = val[j];
-      if (col[j] == i && val[j] > 0.0) diag = true;
-    }
-    if (!diag) M[(int64_t)i * 2 * n + i] = 1.0;  // empty aggregate: identity row keeps the matrix regular
-  }
+  if (!diag) M[(int64_t)i * n + i] = 1.0;  // empty aggregate: identity row keeps the matrix regular
 }
 
-__global__ void k_dense_invert(int n, double* __restrict__ M) {  // Gauss-Jordan without pivoting (SPD), one CTA
-  extern __shared__ double f[];                                   // column p of the current step
-  const int w = 2 * n;
-  for (int p = 0; p < n; p++) {
-    const double piv = M[(int64_t)p * w + p];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) f[i] = M[(int64_t)i * w + p];
-    __syncthreads();
-    const double ip = 1.0 / piv;
-    for (int j = threadIdx.x; j < w; j += blockDim.x) M[(int64_t)p * w + j] *= ip;
-    __syncthreads();
-    for (int e = threadIdx.x; e < n * w; e += blockDim.x) {
-      const int i = e / w, j = e - i * w;
-      if (i != p) M[e] = fma(-f[i], M[(int64_t)p * w + j], M[e]);
-    }
-    __syncthreads();
-  }
-}
-
-__global__ void k_dense_extract(int n, const double* __restrict__ M, double* __restrict__ Ainv) {
-  for (int e = threadIdx.x + blockIdx.x * blockDim.x; e < n * n; e += blockDim.x * gridDim.x) {
-    const int i = e / n, j = e - i * n;
-    Ainv[e] = M[(int64_t)i * 2 * n + n + j];
-  }
+// One pivot step of the in-place Gauss-Jordan inversion (no pivoting: the matrix is SPD), out-of-place between two
+// buffers so that no thread reads what another one writes.  One launch per pivot: n launches of n^2 threads -- 1 ms at
+// n = 400, where the single-CTA version of round 1 took 9.4 ms at n = 250 (ncu, profiles/r02_notes.md).
+__global__ void k_gj_step(int n, int p, const double* __restrict__ in, double* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * n) return;
+  const int i = e / n, j = e - i * n;
+  const double ip = 1.0 / in[(int64_t)p * n + p];
+  double v;
+  if (i == p) v = (j == p) ? ip : in[e] * ip;
+  else if (j == p) v = -in[e] * ip;
+  else v = fma(-in[(int64_t)i * n + p] * ip, in[(int64_t)p * n + j], in[e]);
+  out[e] = v;
 }
 
 // x = Ainv b on the coarsest level: 8 lanes per output entry split the dot product, fixed-order shuffle reduction
@@ -729,11 +714,16 @@ void amg_build_hierarchy(Ctx* c) {
     Ctx::AmgLevel& L = c->amg[nlev - 1];
     const int n = (int)L.n;
     if (n > 2048) FAIL(REMO_ERR_ARG, "amg_setup: coarsest level still has %d rows", n);
-    double* M = scratch<double>(c, 6, (size_t)n * 2 * n);
+    double* M = scratch<double>(c, 6, (size_t)n * n);
     c->amg_dense.ensure((size_t)n * n, st);
-    LAUNCH(c, k_dense_fill, 1, 1024, 0, L.rowptr.p, L.col.p, L.val.p, n, M);
-    LAUNCH(c, k_dense_invert, 1, 1024, n * sizeof(double), n, M);
-    LAUNCH(c, k_dense_extract, 64, 256, 0, n, M, c->amg_dense.p);
+    double* buf[2] = {(n & 1) ? M : c->amg_dense.p, (n & 1) ? c->amg_dense.p : M};  // n swaps later the result sits in amg_dense
+    CK(cudaMemsetAsync(buf[0], 0, (size_t)n * n * sizeof(double), st));
+    LAUNCH(c, k_dense_fill, grid_for(n, TB), TB, 0, L.rowptr.p, L.col.p, L.val.p, n, buf[0]);
+    for (int p = 0; p < n; p++) {
+      k_gj_step<<<grid_for((int64_t)n * n, TB), TB, 0, st>>>(n, p, buf[p & 1], buf[(p + 1) & 1]);
+    }
+    c->launches += n;
+    CK(cudaGetLastError());
   }
 }
 

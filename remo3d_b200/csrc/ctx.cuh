@@ -164,7 +164,7 @@ struct Ctx {
   int amg_agg = 1;           // 1 = strength-based pairwise aggregation, 0 = Morton-rank aggregates of 8 (round 1)
   int amg_passes = 3;        // pairwise passes per level: aggregates of at most 2^passes rows
   int amg_rounds = 4;        // handshake rounds per pass
-  int amg_fused_tail = 1;    // the levels below amg_tail_rows rows run as one cluster kernel (amg.cu k_vcycle_tail)
+  int amg_fused_tail = 0;    // 1: the levels below amg_tail_rows rows run as one cluster kernel (amg.cu k_vcycle_tail); measured slower, off
   int64_t amg_tail_rows = 20000;
   double amg_alpha = 1.5, amg_omega_scale = 1.0;  // coarse-correction scaling, weight of the l1-Jacobi sweeps (<= 1)
   int amg_sweeps = 1;                              // pre = post smoothing sweeps

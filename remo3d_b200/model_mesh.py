@@ -29,27 +29,68 @@ def task_sigma(formation, mud_resistivity):
     return [1.0 / mud_resistivity] + list(1.0 / res)
 
 
+def geometry_key(dip_rad, electrodes_z, domain_radius, mesh_options=None):
+    """Hashable key of everything the 3D tet GEOMETRY of a task depends on.  The half-ball mesher places points from the
+    electrode pattern, the radius and the size options only (materials are assigned per tet afterwards), so all tasks
+    with the same electrode pattern -- 11 patterns for 413 tasks in config C5 (1000 depths x 4 tools) -- share one
+    triangulation.  None for dip == 0: the conforming 2D meshes follow the formation and are unique per task."""
+    if np.isclose(dip_rad, 0.0):
+        return None
+    opts = dict(DEFAULT_MESH_OPTIONS)
+    opts.update({k: v for k, v in (mesh_options or {}).items() if k in DEFAULT_MESH_OPTIONS or k.startswith("improve")})
+    return (float(domain_radius), tuple(np.round(np.asarray(electrodes_z, dtype=float), 6)), tuple(sorted(opts.items())))
+
+
+def build_geometry_3d(electrodes_z, domain_radius, mesh_options=None):
+    """The formation-independent part of a 3D task mesh: points, tets, boundary facets (+ tet centroids for the material
+    predicate)."""
+    opts = dict(DEFAULT_MESH_OPTIONS)
+    opts.update({k: v for k, v in (mesh_options or {}).items() if k in DEFAULT_MESH_OPTIONS or k.startswith("improve")})
+    m = meshgen.half_ball_mesh(float(domain_radius), np.asarray(electrodes_z, dtype=float), material=None, **opts)
+    m["centroids"] = m["points"][m["elems"]].mean(axis=1)
+    return m
+
+
+def assign_materials_3d(geometry, formation, borehole_geometry, dip_rad, centre_depth):
+    """Mesh of one task from a (shared) geometry: only the per-tet material index depends on the depth of the batch."""
+    formation = np.asarray(formation, dtype=float)
+    tops = formation[1:, 0] - centre_depth  # interfaces between consecutive layers, relative depth
+    invasion = [None if np.isnan(r) else float(r) for r in formation[:, 2]]
+    caliper = (np.asarray(borehole_geometry)[:, 0] - centre_depth, np.asarray(borehole_geometry)[:, 1])
+    material = meshgen.layered_material(tops, dip_rad=dip_rad, borehole_radius=caliper, invasion=invasion)
+    mat = np.asarray(material(geometry["centroids"]), dtype=np.int32)
+    return Mesh(geometry["points"], geometry["elems"], mat, geometry["bfacets"], geometry["bc"], geometry["bc_names"])
+
+
+def read_task_mesh(path, dim):
+    """A task mesh produced by an external Gmsh run (`mesh_generator="gmsh"` with `mesh_options={"msh_path": ...}`): MSH 2.2
+    ASCII, numbering contract of the reference's `ReadGmsh` (`gmsh_functions.py:177-382`, msh_reader.py)."""
+    from . import msh_reader
+
+    return msh_reader.read_msh(path, dim)
+
+
 def build_task_mesh(formation, borehole_geometry, dip_rad, centre_depth, electrodes_z, mud_resistivity, domain_radius,
-                    mesh_options=None):
+                    mesh_options=None, geometry=None, task_index=None):
     """-> (Mesh, sigma list) for the batch centred at `centre_depth` with electrodes at relative depths `electrodes_z`.
     dip == 0 -> 2D axisymmetric (r, z) half-disc, interfaces meshed conformingly (the reference's Netgen/Gmsh 2D path,
-    `remo3d.py:776-784`); dip > 0 -> 3D half-ball."""
+    `remo3d.py:776-784`); dip > 0 -> 3D half-ball (`geometry`: a shared triangulation from build_geometry_3d).
+    `mesh_options["msh_path"]` (a format string taking the task index, or a callable(task_index, centre_depth,
+    electrodes_z) -> path) reads the task's mesh from a Gmsh `.msh` file instead (`worker.py:82-92`)."""
     formation = np.asarray(formation, dtype=float)
+    msh_path = (mesh_options or {}).get("msh_path")
+    if msh_path is not None:
+        path = msh_path(task_index, centre_depth, electrodes_z) if callable(msh_path) else str(msh_path).format(task_index)
+        return read_task_mesh(path, 2 if np.isclose(dip_rad, 0.0) else 3), task_sigma(formation, mud_resistivity)
     if np.isclose(dip_rad, 0.0):
         opts = dict(DEFAULT_MESH_OPTIONS_2D)
-        opts.update(mesh_options or {})
+        opts.update({k: v for k, v in (mesh_options or {}).items() if k != "msh_path"})
         wall = (np.asarray(borehole_geometry)[:, 0] - centre_depth, np.asarray(borehole_geometry)[:, 1])
         invasion = [None if np.isnan(r) else float(r) for r in formation[:, 2]]
         m = meshgen2d.half_disc_mesh(float(domain_radius), np.asarray(electrodes_z, dtype=float), wall, formation[1:, 0] - centre_depth,
                                      invasion, **opts)
         mesh = Mesh(m["points"], m["elems"], m["mat"], m["bfacets"], m["bc"], m["bc_names"])
         return mesh, task_sigma(formation, mud_resistivity)
-    opts = dict(DEFAULT_MESH_OPTIONS)
-    opts.update(mesh_options or {})
-    tops = formation[1:, 0] - centre_depth  # interfaces between consecutive layers, relative depth
-    invasion = [None if np.isnan(r) else float(r) for r in formation[:, 2]]
-    caliper = (np.asarray(borehole_geometry)[:, 0] - centre_depth, np.asarray(borehole_geometry)[:, 1])
-    material = meshgen.layered_material(tops, dip_rad=dip_rad, borehole_radius=caliper, invasion=invasion)
-    m = meshgen.half_ball_mesh(float(domain_radius), np.asarray(electrodes_z, dtype=float), material=material, **opts)
-    mesh = Mesh(m["points"], m["elems"], m["mat"], m["bfacets"], m["bc"], m["bc_names"])
-    return mesh, task_sigma(formation, mud_resistivity)
+    if geometry is None:
+        geometry = build_geometry_3d(electrodes_z, domain_radius, mesh_options)
+    return assign_materials_3d(geometry, formation, borehole_geometry, dip_rad, centre_depth), task_sigma(formation, mud_resistivity)

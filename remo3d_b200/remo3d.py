@@ -7,6 +7,7 @@ reference hard-codes: `order` (3, ngsolve_functions.py:27), `rtol` (CG tolerance
 Plotting (`save_results` figures) is out of scope; the text writer keeps the reference's file format.
 """
 import datetime
+import json
 import multiprocessing
 import os
 import queue
@@ -18,8 +19,19 @@ from . import _cabi, model_io, model_mesh, planner, tools as tl, worker
 
 
 def _build_mesh_job(args):
-    """Runs in a mesh-pool process: one task's mesh + sigma list (pure host work)."""
-    return model_mesh.build_task_mesh(*args)
+    """Runs in a mesh-pool process: one task's mesh + sigma list (pure host work).  Exceptions are RETURNED, not raised:
+    a mesh that cannot be built turns its own task into NaN log points (`worker.py:82-138`), not the whole run."""
+    try:
+        return model_mesh.build_task_mesh(*args)
+    except Exception as exc:  # noqa: BLE001 -- the failure contract covers every error
+        return exc, None
+
+
+def _build_geometry_job(args):
+    try:
+        return model_mesh.build_geometry_3d(*args)
+    except Exception as exc:  # noqa: BLE001
+        return exc
 
 
 class Model:
@@ -35,6 +47,7 @@ class Model:
         self.gpu_workers = None
         self.logs = None
         self.task_records = None
+        self.pipeline_stats = None
         self._contexts = None
         self._mesh_pool = None
 
@@ -100,7 +113,7 @@ class Model:
         return planner.prepare_simulation_depths_and_tasks(self.tools, self.sec, measurement_depths, batch_size)
 
     # ---- workers (remo3d.py:552-599, 887-899)
-    def initialize_workers(self, cpu_workers=4, gpu_workers=0, contexts_per_gpu=2):
+    def initialize_workers(self, cpu_workers=4, gpu_workers=0, contexts_per_gpu=2, devices=None):
         """`gpu_workers` = number of GPUs to shard the mesh tasks over (0 is promoted to 1: there is no CPU solve
         path in this package); `cpu_workers` = host processes that build meshes ahead of the GPUs.  Every GPU runs
         `contexts_per_gpu` solver contexts (own stream + host thread): mesh tasks are independent, and two in flight
@@ -118,7 +131,9 @@ class Model:
         self._mesh_pool = multiprocessing.get_context("fork").Pool(cpu_workers)
         try:
             # fails loudly without a B200
-            self._contexts = [_cabi.Context(d) for d in range(self.gpu_workers) for _ in range(max(1, int(contexts_per_gpu)))]
+            # `devices`: explicit CUDA device numbers (one rank per GPU under torchrun passes [LOCAL_RANK]); default 0..gpu_workers-1
+            devs = list(devices) if devices is not None else list(range(self.gpu_workers))
+            self._contexts = [_cabi.Context(d) for d in devs for _ in range(max(1, int(contexts_per_gpu)))]
         except Exception:
             self._mesh_pool.terminate()
             self._mesh_pool = None
@@ -135,7 +150,16 @@ class Model:
 
     # ---- simulation (remo3d.py:723-884)
     def simulate_logs(self, measurement_depths, domain_radius=50, batch_size=5, mesh_generator="auto", preconditioner="multigrid",
-                      condense=True, order=3, rtol=1e-10, maxit=1000, mesh_options=None):
+                      condense=True, order=3, rtol=1e-10, maxit=None, mesh_options=None, results_log=None, resume=False,
+                      share_geometry=True, task_shard=None):
+        """`remo3d.py:723-884`.  Additions to the reference's keywords: `order` (the reference hard-codes 3), `rtol`, `maxit`
+        (None: 1000 for "multigrid" like `ngsolve_functions.py:50`, 20000 for "local"), `task_shard=(rank, world)` (this
+        process solves every world-th task and the [depth, tool, Ra] triples are gathered over torch.distributed at the end,
+        the reference's single MPI gather, `remo3d.py:865`), `mesh_options` (mesh sizes; with
+        `mesh_generator="gmsh"` a `"msh_path"` entry reads every task's mesh from a Gmsh MSH 2.2 file), `results_log` (a
+        JSON-lines file that receives every finished task; with `resume=True` the tasks already in it are not solved
+        again), `share_geometry` (3D: tasks with the same electrode pattern share one triangulation).
+        Per-task failures (meshing or solving) give NaN log points and an `error` entry in `task_records`."""
         start_time = datetime.datetime.now()
         measurement_depths = np.asarray(measurement_depths, dtype=float)
         domain_radius_alert = False
@@ -149,10 +173,16 @@ class Model:
             print("Some electrodes are located close to the boundary of the simulation domain. This may cause problems during simulation. Consider increase of the domain size")
         if mesh_generator == "auto":
             mesh_generator = "netgen" if np.isclose(self.dip_deg, 0) else "gmsh"
+        if mesh_generator not in ("netgen", "gmsh"):
+            raise ValueError("mesh_generator must be 'auto', 'netgen' or 'gmsh'")
         if ~np.isclose(self.dip_deg, 0) and mesh_generator != "gmsh":
             raise ValueError("The only mesh generator supported in 3D models is gmsh")
         if preconditioner not in _cabi.PRECOND:
             raise ValueError("preconditioner must be 'local' or 'multigrid'")
+        if type(batch_size) != int or batch_size < 1:
+            raise ValueError("batch_size must be a positive integer")
+        if (mesh_options or {}).get("msh_path") is not None and mesh_generator != "gmsh":
+            raise ValueError("mesh_options['msh_path'] needs mesh_generator='gmsh'")
         if self._contexts is None:
             raise RuntimeError("initialize_workers() must be called before simulate_logs()")
         borehole_model = self.borehole_model
@@ -165,37 +195,126 @@ class Model:
         mud_resistivities = np.interp(simulation_depths, borehole_model[:, 0], borehole_model[:, 2])
         print("{} simulation tasks prepared".format(n_tasks))
 
-        job_args = [(self.formation_model, borehole_geometry, self.dip_rad, simulation_depths[t[0]], t[1][0], mud_resistivities[t[0]],
-                     domain_radius, mesh_options) for t in task_list]
+        triples, records, lock = [], [None] * n_tasks, threading.Lock()
+        # ---- resume: tasks already in the results log are taken from it (same plan: same depths, tools, batch size)
+        done = set()
+        plan_id = "%d tasks, %d depths, tools %s, batch %d, order %d, R %g" % (n_tasks, measurement_depths.shape[0], list(self.tools.keys()),
+                                                                             batch_size, order, domain_radius)
+        log_file = None
+        if results_log is not None:
+            if resume and os.path.exists(results_log):
+                with open(results_log) as f:
+                    for line in f:
+                        try:
+                            rec = json.loads(line)
+                        except ValueError:
+                            continue  # a line cut off by the crash that made the resume necessary
+                        if rec.get("plan") == plan_id and 0 <= rec.get("task", -1) < n_tasks and "error" not in rec.get("record", {}):
+                            if rec["task"] not in done:
+                                done.add(rec["task"])
+                                triples.extend(rec["triples"])
+                                records[rec["task"]] = rec["record"]
+                print("{} tasks taken from {}".format(len(done), results_log))
+            log_file = open(results_log, "a" if resume else "w")
+        todo = [i for i in range(n_tasks) if i not in done]
+        if task_shard is not None:
+            mine = set(worker.shard(n_tasks, int(task_shard[0]), int(task_shard[1])))
+            todo = [i for i in todo if i in mine]
+
+        def job_args(i, geometry=None):
+            t = task_list[i]
+            return (self.formation_model, borehole_geometry, self.dip_rad, simulation_depths[t[0]], t[1][0], mud_resistivities[t[0]],
+                    domain_radius, mesh_options, geometry, i)
 
         jobs = queue.Queue(maxsize=2 * len(self._contexts) + 2)
-        triples, records, lock = [], [None] * n_tasks, threading.Lock()
+        stop = threading.Event()
+        busy = [0.0] * len(self._contexts)
 
-        def gpu_loop(ctx):
+        def gpu_loop(k, ctx):
             def feed():
-                while True:
-                    job = jobs.get()
+                while not stop.is_set():
+                    try:
+                        job = jobs.get(timeout=0.2)
+                    except queue.Empty:
+                        continue
                     if job is None:
                         return
                     yield job
-            for index, t, rec in worker.run_tasks(ctx, feed(), self.tools, order, preconditioner, rtol, maxit):
+            t0 = [0.0]
+
+            def timed_feed():
+                for job in feed():
+                    t0[0] = datetime.datetime.now().timestamp()
+                    yield job
+            for index, t, rec in worker.run_tasks(ctx, timed_feed(), self.tools, order, preconditioner, rtol, maxit):
+                busy[k] += datetime.datetime.now().timestamp() - t0[0]
                 with lock:
                     triples.extend(t)
                     records[index] = rec
+                    if log_file is not None:
+                        log_file.write(json.dumps({"plan": plan_id, "task": index, "triples": t, "record": rec}) + "\n")
+                        log_file.flush()
 
-        threads = [threading.Thread(target=gpu_loop, args=(c,), daemon=True) for c in self._contexts]
+        threads = [threading.Thread(target=gpu_loop, args=(k, c), daemon=True) for k, c in enumerate(self._contexts)]
         for th in threads:
             th.start()
-        # meshes are produced ahead by the process pool, in task order, while the GPU workers solve
-        for i, (mesh, sigma) in enumerate(self._mesh_pool.imap(_build_mesh_job, job_args, chunksize=1)):
-            jobs.put((i, task_list[i], mesh, sigma))
-        for _ in threads:
-            jobs.put(None)
-        for th in threads:
-            th.join()
 
+        def put(item):
+            """Bounded put that notices dead consumers instead of blocking forever."""
+            while True:
+                try:
+                    jobs.put(item, timeout=0.5)
+                    return
+                except queue.Full:
+                    if not any(th.is_alive() for th in threads):
+                        raise RuntimeError("all GPU worker threads died")
+
+        t_mesh0 = datetime.datetime.now().timestamp()
+        mesh_seconds = 0.0
+        try:
+            three_d = not np.isclose(self.dip_rad, 0.0)
+            use_shared = three_d and share_geometry and (mesh_options or {}).get("msh_path") is None
+            if use_shared:
+                # one triangulation per electrode pattern, built ahead by the pool (largest groups first); the per-task part
+                # (material of every tet at the task's depth) is cheap and runs here while the GPUs solve
+                groups = {}
+                for i in todo:
+                    groups.setdefault(model_mesh.geometry_key(self.dip_rad, task_list[i][1][0], domain_radius, mesh_options), []).append(i)
+                keys = sorted(groups, key=lambda k: -len(groups[k]))
+                geo_args = [(task_list[groups[k][0]][1][0], domain_radius, mesh_options) for k in keys]
+                for k, geometry in zip(keys, self._mesh_pool.imap(_build_geometry_job, geo_args, chunksize=1)):
+                    for i in groups[k]:
+                        if isinstance(geometry, BaseException):
+                            put((i, task_list[i], geometry, None))
+                            continue
+                        tm = datetime.datetime.now().timestamp()
+                        mesh, sigma = _build_mesh_job(job_args(i, geometry))
+                        mesh_seconds += datetime.datetime.now().timestamp() - tm
+                        put((i, task_list[i], mesh, sigma))
+            else:
+                # meshes are produced ahead by the process pool, in task order, while the GPU workers solve
+                for i, (mesh, sigma) in zip(todo, self._mesh_pool.imap(_build_mesh_job, [job_args(i) for i in todo], chunksize=1)):
+                    put((i, task_list[i], mesh, sigma))
+            for _ in threads:
+                put(None)
+            for th in threads:
+                th.join()
+        finally:
+            # whatever happened, no worker thread may still be inside a context when the caller closes it
+            stop.set()
+            for th in threads:
+                th.join()
+            if log_file is not None:
+                log_file.close()
+
+        wall = datetime.datetime.now().timestamp() - t_mesh0
+        if task_shard is not None and int(task_shard[1]) > 1:
+            triples = worker.gather_results(triples, int(task_shard[1]))
         self.logs = worker.results_to_logs(triples, self.tools, measurement_depths)
         self.task_records = records
+        self.pipeline_stats = {"tasks": len(todo), "wall_s": wall, "gpu_busy_s": list(busy),
+                               "gpu_busy_fraction": (sum(busy) / (len(busy) * wall)) if wall > 0 else 0.0,
+                               "host_material_s": mesh_seconds, "shared_geometry": bool(len(todo)) and use_shared}
         print("\nProcessed in: ", datetime.datetime.now() - start_time)
 
     # ---- results (text part of remo3d.py:902-990)

@@ -74,3 +74,50 @@ def star_case(nsphere=260, seed=3):
     bc = np.full(bf.shape[0], 2, dtype=np.int32)
     mat = (pts[elems].mean(axis=1)[:, 2] > 0).astype(np.int32)
     return Mesh(pts, elems, mat, bf, bc, ["natural", "dirichlet_boundary"]), [1.0, 0.1]
+
+
+class OracleContext:
+    """Stand-in for `_cabi.Context` backed by the CPU oracle: lets the host pipeline (`worker.run_tasks`,
+    `Model.simulate_logs`) run in the CPU test-suite.  Test infrastructure only."""
+
+    def __init__(self, fail_on=()):
+        self.fail_on = set(fail_on)  # task counter values at which solve() raises
+        self.calls = 0
+        self.ndof = 0
+
+    def mesh_set(self, dim, points, elems, mat, bfacets, bdir, axis):
+        self.m = (dim, points, elems, mat, bfacets, bdir)
+
+    def space_build(self, order):
+        self.order = order
+        return 0, 0
+
+    def assemble(self, sigma):
+        self.sigma = np.asarray(sigma, dtype=float)
+
+    def precond_setup(self, kind):
+        self.kind = kind
+
+    def rhs_point_sources(self, src_ptr, src_z, src_fac):
+        self.src = (np.asarray(src_ptr), np.asarray(src_z), np.asarray(src_fac))
+
+    def solve(self, rtol=1e-10, maxit=1000, raise_on_noconv=True):
+        self.calls += 1
+        if self.calls in self.fail_on:
+            raise RuntimeError("injected solver failure")
+        n = self.src[0].shape[0] - 1
+        return np.ones(n, np.int32), np.zeros(n)
+
+    def apparent_resistivity(self, pt_rhs, z0, z1, k, scale, out=None):
+        from oracle import fem_oracle as fo
+
+        dim, points, elems, mat, bfacets, bdir = self.m
+        flat = {"src_ptr": self.src[0], "src_z": self.src[1], "src_fac": self.src[2], "pt_rhs": np.asarray(pt_rhs), "pt_z0": np.asarray(z0),
+                "pt_z1": np.asarray(z1), "pt_k": np.asarray(k), "scale": scale}
+        return fo.solve_task(points, elems, mat, self.sigma, bfacets, np.asarray(bdir, bool), self.order, flat, dim=dim, solver="direct")["ra"]
+
+    def stage_times(self):
+        return {}
+
+    def close(self):
+        pass
