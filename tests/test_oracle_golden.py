@@ -4,7 +4,8 @@
 the reference with Netgen 2D meshes, order-3 H1 and NGSolve's PCG.  Here the same inputs go through this repo's host logic
 (tool parser, planner, sigma ordering), this repo's conforming 2D mesher and the CPU oracle (order 3, axisymmetric form
 2 pi r sigma grad u . grad v).  Netgen's meshes are not reproducible, so agreement is expected at the reference's own
-mesh-noise level: its two shipped examples differ from each other by up to 3.1e-4; we measure <= 2.5e-3."""
+mesh-noise level: its two shipped examples differ from each other by up to 3.1e-4; we measure <= 8e-4 (the
+far field of the 2D meshes must be fine for that: meshgen2d h_max, profiles/r02_notes.md)."""
 import os
 
 import numpy as np
@@ -12,11 +13,23 @@ import numpy as np
 from oracle import fem_oracle as fo
 from remo3d_b200 import meshgen2d, model_io, model_mesh, planner, tools as tl
 
-TOOLS = ["A2.0M0.5N", "N0.5M2.0A", "M1.0A0.1B", "B5.7A0.4M"]
-DEPTHS = np.array([5.5, 6.0, 15.0, 15.5])
+TOOLS = ["B5.7A0.4M", "B4.48A1.62M", "M1.0A0.1B", "A2.0M0.5N", "N0.5M2.0A", "M4.0A0.5B"]  # Example_01.py: all six
+DEPTHS = np.array([0.0, 3.0, 4.5, 5.5, 8.4, 10.0, 12.5, 15.0, 18.2, 21.5, 25.0])  # top of the log (where the far field of the mesh matters), thick beds, bed boundaries
+TOL = 1.5e-3  # measured 8e-4 over 51 depths x 6 tools (profiles/r02_notes.md); the reference's own two examples differ by 3.1e-4
+
+
+def _solve_one(args):
+    formation, borehole, centre, task, mud, params = args
+    mesh, sigma = model_mesh.build_task_mesh(formation, borehole[:, :2], 0.0, centre, task[1][0], mud, 50.0)
+    assert mesh.dim == 2
+    flat = planner.flatten_task(task, params, three_d=False)
+    out = fo.solve_task(mesh.points, mesh.elems, mesh.mat, sigma, mesh.bfacets, mesh.dirichlet_flags([2]), 3, flat, dim=2, solver="direct")
+    return [((int(flat["pt_depth"][i]), int(flat["pt_tool"][i])), float(out["ra"][i])) for i in range(flat["pt_rhs"].shape[0])]
 
 
 def test_oracle_reproduces_reference_example01(golden_dir):
+    import multiprocessing
+
     d = os.path.join(golden_dir, "example_01")
     formation = model_io.load_formation_parameters(os.path.join(d, "Formation.txt"))
     borehole = model_io.load_borehole_parameters(os.path.join(d, "Borehole.txt"))
@@ -25,21 +38,17 @@ def test_oracle_reproduces_reference_example01(golden_dir):
     params, sec = tl.set_tools_parameters(TOOLS)
     centres, tasks = planner.prepare_simulation_depths_and_tasks(params, sec, DEPTHS, 5)
     mud = np.interp(centres, borehole[:, 0], borehole[:, 2])  # remo3d.py:806
-    got = {}
-    for task in tasks:
-        mesh, sigma = model_mesh.build_task_mesh(formation, borehole[:, :2], 0.0, centres[task[0]], task[1][0], mud[task[0]], 50.0)
-        assert mesh.dim == 2
-        flat = planner.flatten_task(task, params, three_d=False)
-        out = fo.solve_task(mesh.points, mesh.elems, mesh.mat, sigma, mesh.bfacets, mesh.dirichlet_flags([2]), 3, flat, dim=2, solver="direct")
-        for i in range(flat["pt_rhs"].shape[0]):
-            got[(int(flat["pt_depth"][i]), int(flat["pt_tool"][i]))] = out["ra"][i]
+    jobs = [(formation, borehole, centres[t[0]], t, mud[t[0]], params) for t in tasks]
+    with multiprocessing.get_context("fork").Pool(min(8, os.cpu_count() or 2)) as pool:
+        got = dict(kv for part in pool.map(_solve_one, jobs, chunksize=1) for kv in part)
     worst = 0.0
     for ti, t in enumerate(TOOLS):
         col = names.index(t) + 1
         ref = np.array([gold[np.argmin(np.abs(gold[:, 0] - z)), col] for z in DEPTHS])
         mine = np.array([got[(di, ti)] for di in range(DEPTHS.shape[0])])
         worst = max(worst, float(np.max(np.abs(mine - ref) / ref)))
-    assert worst < 4e-3, worst
+    print('worst relative difference to the reference output', worst)
+    assert worst < TOL, worst
 
 
 def test_2d_mesher_is_conforming():
@@ -54,3 +63,35 @@ def test_2d_mesher_is_conforming():
     zs = mesh.points[mesh.axis_vertices(), 1]
     for z in np.concatenate([flat["src_z"], flat["pt_z0"]]):
         assert np.min(np.abs(zs - z)) < 1e-12
+
+
+THIN = ["A0.4M6.0N", "A1.62M6.0N", "A4.0M0.5N", "A8.0M1.0N"]
+
+
+def test_oracle_reproduces_thin_bedded_benchmark(golden_dir):
+    """`Examples/Benchmark models/Thin-bedded model/Logs/Logs {1, 4}/Results_1.txt` (140 / 200 beds of ~0.125 m, both formation
+    files, aligned and shifted depths) through this repo's host pipeline with the oracle as the solver.  Bounds per tool as in
+    tests/test_gpu_reference_logs.py (the long lateral A8.0M1.0N carries a systematic +2-4 %, see there)."""
+    import multiprocessing
+
+    from remo3d_b200 import Model
+    from tests import helpers
+
+    d = os.path.join(golden_dir, "thin_bedded")
+    shifts = np.loadtxt(os.path.join(d, "Logs_depth_shifts.txt"), skiprows=2)
+    for logs, form, col in ((1, 1, 0), (4, 2, 1)):
+        gold = np.loadtxt(os.path.join(d, "Logs_%d_Results_1.txt" % logs), skiprows=2)[5::14]
+        depths = shifts[5::14, col]
+        m = Model(THIN)
+        m.set_model_parameters(os.path.join(d, "Formation_model_%d.txt" % form), os.path.join(d, "Borehole_model_correct_rm.txt"))
+        m.cpu_workers, m.gpu_workers = 4, 1
+        m._mesh_pool = multiprocessing.get_context("fork").Pool(4)
+        m._contexts = [helpers.OracleContext() for _ in range(min(8, os.cpu_count() or 2))]
+        try:
+            m.simulate_logs(depths)
+        finally:
+            m._mesh_pool.terminate()
+            m._contexts = None
+        for k, (t, tol) in enumerate(zip(THIN, (3.5e-3, 1.2e-2, 2.2e-2, 6e-2))):
+            rel = np.abs(m.logs[t][:, 1] - gold[:, k + 1]) / gold[:, k + 1]
+            assert rel.max() < tol, (logs, t, rel)
