@@ -543,7 +543,10 @@ def run_pipeline(args):
     model.set_model_parameters(formation, borehole, dip=30)
     cpu = max(1, (os.cpu_count() or 1) // world)
     model.initialize_workers(cpu_workers=cpu, gpu_workers=1, devices=[local], contexts_per_gpu=args.contexts)
-    opts = {"h_electrode": he, "h_axis": ha, "grading": g, "h_max": hm, "improve": mesh_rounds() if args.pipeline_improve else 0}
+    # --pipeline-conforming 1: every task meshes its own interfaces (the Model default, reference-like); 0: one triangulation
+    # per electrode pattern, materials per tet centroid (the host-light mode the sharing was built for)
+    opts = {"h_electrode": he, "h_axis": ha, "grading": g, "h_max": hm, "improve": mesh_rounds() if args.pipeline_improve else 0,
+            "conforming": bool(args.pipeline_conforming)}
     try:
         # warm-up: one small call (CUDA context, kernels, pool processes), untimed
         model.simulate_logs(depths[:2], order=args.order, preconditioner=args.preconditioner, mesh_options=dict(opts, h_electrode=0.1, h_axis=0.4, grading=0.6, improve=0))
@@ -578,7 +581,7 @@ def run_pipeline(args):
                            "ndof_median": float(np.median([r["ndof"] for r in recs])) if recs else None,
                            "iterations_median": float(np.median([max(r["iters"]) for r in recs])) if recs else None,
                            "gpu_busy_fraction": busy, "host_material_s_rank0": st["host_material_s"], "shared_geometry": st["shared_geometry"],
-                           "cpu_workers_per_rank": cpu, "contexts_per_gpu": args.contexts, "mesh_sliver_pass_rounds": opts["improve"],
+                           "cpu_workers_per_rank": cpu, "contexts_per_gpu": args.contexts, "conforming_interfaces": bool(args.pipeline_conforming), "mesh_sliver_pass_rounds": opts["improve"],
                            "solve_ms_median": float(np.median([r["solve"] for r in recs])) if recs else None,
                            "timing": "wall clock around simulate_logs (host work is part of the measurement), max over ranks"}}
         emit(line)
@@ -637,11 +640,12 @@ def main():
     ap.add_argument("--maxit", type=int, default=20000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-companions", action="store_true", help="skip the plain-mesh and like-for-like GPU legs (N = 1 only)")
-    ap.add_argument("--contexts", type=int, default=2, help="solver contexts (stream + host thread) per GPU")
+    ap.add_argument("--contexts", type=int, default=3, help="solver contexts (stream + host thread) per GPU")
     ap.add_argument("--mode", default="step", choices=["step", "pipeline"])
     ap.add_argument("--pipeline-depths", type=int, default=1000)
     ap.add_argument("--pipeline-size", default="200k", choices=list(SIZES))
     ap.add_argument("--pipeline-improve", type=int, default=0)
+    ap.add_argument("--pipeline-conforming", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -228,11 +228,19 @@ __global__ void k_coarse_cols(const uint64_t* __restrict__ ukeys, int64_t nnz, i
 // mode 0: OUT = X + omega * dinv * (B - A X)    (l1-Jacobi sweep)      mode 1: OUT = B - A X   (residual)
 // Same lane layout as the PCG SpMM (solver.cu k_spmm_p): a G-lane group owns a row, every lane owns two adjacent
 // right-hand sides (16-byte gathers; ks even) -- or one when ks == 1.
-template <int G, int KP2, int W>
+template <typename T> struct Pair2;
+template <> struct Pair2<double> { using type = double2; };
+template <> struct Pair2<float> { using type = float2; };
+
+// T = storage type of the level (matrix values, dinv, X): double, or float for the mixed-precision cycle
+// (remo_set_option("amg_fp32", 1), the default): TBt / TOt = types of B and OUT -- on level 0 those are the PCG's own fp64
+// blocks R / Z, so the conversion happens inside the sweeps and costs no extra pass.  Sums are taken in T.
+template <int G, int KP2, int W, typename T, typename TBt, typename TOt>
 __global__ void __launch_bounds__(TB) k_smooth(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                               const double* __restrict__ val, const double* __restrict__ dinv,
-                                               const double* __restrict__ B, const double* __restrict__ X,
-                                               double* __restrict__ OUT, int ks, int64_t n, double omega, int mode) {
+                                               const T* __restrict__ val, const T* __restrict__ dinv,
+                                               const TBt* __restrict__ B, const T* __restrict__ X,
+                                               TOt* __restrict__ OUT, int ks, int64_t n, T omega, int mode) {
+  using P2 = typename Pair2<T>::type;
   constexpr int J = G / KP2;
   constexpr int GROUPS = TB / G;
   const int lane = threadIdx.x & 31;
@@ -243,18 +251,18 @@ __global__ void __launch_bounds__(TB) k_smooth(const int64_t* __restrict__ rowpt
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((lane / G) * G));
   for (int64_t row = (int64_t)blockIdx.x * GROUPS + grp; row < n; row += (int64_t)gridDim.x * GROUPS) {
     const int64_t s = rowptr[row], e = rowptr[row + 1];
-    double acc0 = 0.0, acc1 = 0.0;
+    T acc0 = 0, acc1 = 0;
     for (int64_t base = s; base < e; base += G) {
       int32_t myc = (int32_t)row;
-      double myv = 0.0;
+      T myv = 0;
       if (base + gl < e) { myc = col[base + gl]; myv = val[base + gl]; }
 #pragma unroll
       for (int i = 0; i < KP2; i++) {
         const int j = i * J + jsub;
         const int32_t c = __shfl_sync(gmask, myc, j, G);
-        const double v = __shfl_sync(gmask, myv, j, G);
+        const T v = __shfl_sync(gmask, myv, j, G);
         if (W == 2) {
-          const double2 x = *reinterpret_cast<const double2*>(X + (int64_t)c * ks + cc);
+          const P2 x = *reinterpret_cast<const P2*>(X + (int64_t)c * ks + cc);
           acc0 = fma(v, x.x, acc0);
           acc1 = fma(v, x.y, acc1);
         } else {
@@ -269,45 +277,68 @@ __global__ void __launch_bounds__(TB) k_smooth(const int64_t* __restrict__ rowpt
     }
     if (jsub == 0 && on) {
       const int64_t idx = row * ks + cc;
-      const double w = omega * dinv[row];
-      const double res0 = B[idx] - acc0;
-      OUT[idx] = (mode == 1) ? res0 : fma(w, res0, X[idx]);
+      const T w = omega * dinv[row];
+      const T res0 = (T)B[idx] - acc0;
+      OUT[idx] = (TOt)((mode == 1) ? res0 : fma(w, res0, X[idx]));
       if (W == 2) {
-        const double res1 = B[idx + 1] - acc1;
-        OUT[idx + 1] = (mode == 1) ? res1 : fma(w, res1, X[idx + 1]);
+        const T res1 = (T)B[idx + 1] - acc1;
+        OUT[idx + 1] = (TOt)((mode == 1) ? res1 : fma(w, res1, X[idx + 1]));
       }
     }
   }
 }
 
-__global__ void k_jacobi0(const double* __restrict__ dinv, const double* __restrict__ B, double* __restrict__ X, int k, int64_t n,
-                          double omega) {
+template <typename T, typename TBt>
+__global__ void k_jacobi0(const T* __restrict__ dinv, const TBt* __restrict__ B, T* __restrict__ X, int k, int64_t n, T omega) {
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= n * k) return;
-  X[e] = omega * dinv[e / k] * B[e];
+  X[e] = omega * dinv[e / k] * (T)B[e];
 }
 
 // rows of an aggregate in ascending order (members / aggptr): fixed summation order -> bit-reproducible
-__global__ void k_restrict(const int32_t* __restrict__ aggptr, const int32_t* __restrict__ members, const double* __restrict__ R,
-                           double* __restrict__ BC, int k, int64_t nc) {
+template <typename T>
+__global__ void k_restrict(const int32_t* __restrict__ aggptr, const int32_t* __restrict__ members, const T* __restrict__ R,
+                           T* __restrict__ BC, int k, int64_t nc) {
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= nc * k) return;
   const int64_t a = e / k;
   const int r = (int)(e - a * k);
-  double s = 0.0;
+  T s = 0;
   for (int32_t p = aggptr[a]; p < aggptr[a + 1]; p++) s += R[(int64_t)members[p] * k + r];
   BC[e] = s;
 }
 
-__global__ void k_prolong(const int32_t* __restrict__ agg, const double* __restrict__ dinv, const double* __restrict__ XC,
-                          double* __restrict__ X, int k, int64_t n, double alpha) {
+template <typename T>
+__global__ void k_prolong(const int32_t* __restrict__ agg, const T* __restrict__ dinv, const T* __restrict__ XC,
+                          T* __restrict__ X, int k, int64_t n, T alpha) {
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= n * k) return;
   const int64_t i = e / k;
   const int r = (int)(e - i * k);
   const int32_t a = agg[i];
-  if (a < 0 || dinv[i] == 0.0) return;  // constrained / empty rows stay zero
+  if (a < 0 || dinv[i] == (T)0) return;  // constrained / empty rows stay zero
   X[e] = fma(alpha, XC[(int64_t)a * k + r], X[e]);
+}
+
+// x = Ainv b on the coarsest level (the inverse stays fp64; vectors in T): 8 lanes per output entry split the dot product
+template <typename T>
+__global__ void k_dense_apply_t(int n, const double* __restrict__ Ainv, const T* __restrict__ B, T* __restrict__ X, int k) {
+  const int t = threadIdx.x + blockIdx.x * blockDim.x;
+  const int e = t >> 3, part = t & 7;
+  double s = 0.0;
+  const bool ok = e < n * k;
+  const int i = ok ? e / k : 0, r = ok ? e - i * k : 0;
+  if (ok)
+    for (int j = part; j < n; j += 8) s = fma(Ainv[(int64_t)i * n + j], (double)B[(int64_t)j * k + r], s);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  if (ok && part == 0) X[e] = (T)s;
+}
+
+__global__ void k_to_float(const double* __restrict__ in, float* __restrict__ out, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
 }
 
 // ---------------------------------------------------------------- coarsest level: dense inverse
@@ -338,21 +369,6 @@ __global__ void k_gj_step(int n, int p, const double* __restrict__ in, double* _
   out[e] = v;
 }
 
-// x = Ainv b on the coarsest level: 8 lanes per output entry split the dot product, fixed-order shuffle reduction
-__global__ void k_dense_apply(int n, const double* __restrict__ Ainv, const double* __restrict__ B, double* __restrict__ X, int k) {
-  const int t = threadIdx.x + blockIdx.x * blockDim.x;
-  const int e = t >> 3, part = t & 7;
-  double s = 0.0;
-  const bool ok = e < n * k;
-  const int i = ok ? e / k : 0, r = ok ? e - i * k : 0;
-  if (ok)
-    for (int j = part; j < n; j += 8) s = fma(Ainv[(int64_t)i * n + j], B[(int64_t)j * k + r], s);
-  s += __shfl_xor_sync(0xffffffffu, s, 4);
-  s += __shfl_xor_sync(0xffffffffu, s, 2);
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  if (ok && part == 0) X[e] = s;
-}
-
 // ---------------------------------------------------------------- the small levels of the V-cycle in ONE launch
 // Below ~16 k rows a level's kernels are pure launch latency (5 launches of 3-10 us per level and V-cycle, ~25 launches
 // = ~120 us of a 1.3 ms PCG iteration at 4.8 M dofs).  k_vcycle_tail runs the whole sub-cycle of those levels -- first
@@ -362,33 +378,37 @@ __global__ void k_dense_apply(int n, const double* __restrict__ Ainv, const doub
 // L2.  Same arithmetic as the per-level kernels (k_jacobi0, k_smooth, k_restrict, k_prolong, k_dense_apply), and for the
 // strides 6 and 8 (5..8 right-hand sides: k_smooth<4,4,2>) also the same summation order, i.e. bit-identical results
 // (remo_set_option("amg_fused_tail", 0) selects the per-level launches).  Column pairs: ks even, ks <= 8.
+template <typename T>
 struct TailLevel {
   const int64_t* rowptr;
   const int32_t* col;
-  const double* val;
-  const double* dinv;
+  const T* val;
+  const T* dinv;
   const int32_t* agg;
   const int32_t* aggptr;
   const int32_t* members;
-  const double* b;
-  double* x;
-  double* t;
+  const T* b;
+  T* x;
+  T* t;
   int64_t n;
-  double omega;
+  T omega;
 };
+template <typename T>
 struct TailArgs {
-  TailLevel L[MAXLEV];
+  TailLevel<T> L[MAXLEV];
   int nl;               // levels handled here; the last one is the coarsest (dense inverse)
-  const double* dense;  // inverse of the coarsest matrix
+  const double* dense;  // inverse of the coarsest matrix (fp64 in both precisions)
   int k;                // row stride of the blocks (even, <= 8)
   int sweeps;
-  double alpha;
+  T alpha;
 };
 constexpr int TAIL_CTAS = 8, TAIL_THREADS = 1024;
 
 // OUT = X + omega dinv (B - A X) (mode 0) or B - A X (mode 1): the loop of k_smooth<4, 4, 2> over the cluster's threads
-__device__ __forceinline__ void tail_smooth(const TailLevel& L, const double* __restrict__ X, double* __restrict__ OUT, int ks, int mode,
+template <typename T>
+__device__ __forceinline__ void tail_smooth(const TailLevel<T>& L, const T* __restrict__ X, T* __restrict__ OUT, int ks, int mode,
                                             int ctid, int nthreads) {
+  using P2 = typename Pair2<T>::type;
   constexpr int G = 4;
   const int lane = ctid & 31;
   const int gl = ctid % G;
@@ -398,66 +418,67 @@ __device__ __forceinline__ void tail_smooth(const TailLevel& L, const double* __
   const unsigned gmask = ((1u << G) - 1u) << ((lane / G) * G);
   for (int64_t row = ctid / G; row < L.n; row += nthreads / G) {
     const int64_t s = L.rowptr[row], e = L.rowptr[row + 1];
-    double acc0 = 0.0, acc1 = 0.0;
+    T acc0 = 0, acc1 = 0;
     for (int64_t base = s; base < e; base += G) {
       int32_t myc = (int32_t)row;
-      double myv = 0.0;
+      T myv = 0;
       if (base + gl < e) { myc = L.col[base + gl]; myv = L.val[base + gl]; }
 #pragma unroll
       for (int i = 0; i < G; i++) {
         const int32_t c = __shfl_sync(gmask, myc, i, G);
-        const double v = __shfl_sync(gmask, myv, i, G);
-        const double2 x = *reinterpret_cast<const double2*>(X + (int64_t)c * ks + cc);
+        const T v = __shfl_sync(gmask, myv, i, G);
+        const P2 x = *reinterpret_cast<const P2*>(X + (int64_t)c * ks + cc);
         acc0 = fma(v, x.x, acc0);
         acc1 = fma(v, x.y, acc1);
       }
     }
     if (on) {
       const int64_t idx = row * ks + cc;
-      const double w = L.omega * L.dinv[row];
-      const double res0 = L.b[idx] - acc0, res1 = L.b[idx + 1] - acc1;
+      const T w = L.omega * L.dinv[row];
+      const T res0 = L.b[idx] - acc0, res1 = L.b[idx + 1] - acc1;
       OUT[idx] = (mode == 1) ? res0 : fma(w, res0, X[idx]);
       OUT[idx + 1] = (mode == 1) ? res1 : fma(w, res1, X[idx + 1]);
     }
   }
 }
 
-__global__ void __cluster_dims__(TAIL_CTAS, 1, 1) __launch_bounds__(TAIL_THREADS) k_vcycle_tail(const __grid_constant__ TailArgs a) {
+template <typename T>
+__global__ void __cluster_dims__(TAIL_CTAS, 1, 1) __launch_bounds__(TAIL_THREADS) k_vcycle_tail(const __grid_constant__ TailArgs<T> a) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int ctid = (int)cluster.block_rank() * TAIL_THREADS + threadIdx.x;
   const int nthreads = TAIL_CTAS * TAIL_THREADS;
   const int k = a.k, nl = a.nl;
-  double* xs[MAXLEV];
-  double* ts[MAXLEV];
+  T* xs[MAXLEV];
+  T* ts[MAXLEV];
 #pragma unroll
   for (int l = 0; l < MAXLEV; l++) { xs[l] = a.L[l].x; ts[l] = a.L[l].t; }
   // ---- down
   for (int l = 0; l < nl - 1; l++) {
-    const TailLevel& L = a.L[l];
+    const TailLevel<T>& L = a.L[l];
     for (int64_t e = ctid; e < L.n * k; e += nthreads) xs[l][e] = L.omega * L.dinv[e / k] * L.b[e];
     cluster.sync();
     for (int sw = 1; sw < a.sweeps; sw++) {
-      tail_smooth(L, xs[l], ts[l], k, 0, ctid, nthreads);
-      double* tmp = xs[l]; xs[l] = ts[l]; ts[l] = tmp;
+      tail_smooth<T>(L, xs[l], ts[l], k, 0, ctid, nthreads);
+      T* tmp = xs[l]; xs[l] = ts[l]; ts[l] = tmp;
       cluster.sync();
     }
-    tail_smooth(L, xs[l], ts[l], k, 1, ctid, nthreads);  // t = b - A x
+    tail_smooth<T>(L, xs[l], ts[l], k, 1, ctid, nthreads);  // t = b - A x
     cluster.sync();
-    const TailLevel& C = a.L[l + 1];
-    double* bc = const_cast<double*>(C.b);
+    const TailLevel<T>& C = a.L[l + 1];
+    T* bc = const_cast<T*>(C.b);
     for (int64_t e = ctid; e < C.n * k; e += nthreads) {
       const int64_t ag = e / k;
       const int r = (int)(e - ag * k);
-      double sum = 0.0;
+      T sum = 0;
       for (int32_t p = L.aggptr[ag]; p < L.aggptr[ag + 1]; p++) sum += ts[l][(int64_t)L.members[p] * k + r];
       bc[e] = sum;
     }
     cluster.sync();
   }
-  // ---- coarsest: x = Ainv b, 8 lanes per entry as k_dense_apply
+  // ---- coarsest: x = Ainv b, 8 lanes per entry as k_dense_apply_t
   {
-    const TailLevel& L = a.L[nl - 1];
+    const TailLevel<T>& L = a.L[nl - 1];
     const int n = (int)L.n;
     for (int base = 0; base < n * k * 8; base += nthreads) {
       const int t = base + ctid;
@@ -466,28 +487,28 @@ __global__ void __cluster_dims__(TAIL_CTAS, 1, 1) __launch_bounds__(TAIL_THREADS
       const bool ok = e < n * k;
       const int i = ok ? e / k : 0, r = ok ? e - i * k : 0;
       if (ok)
-        for (int j = part; j < n; j += 8) sum = fma(a.dense[(int64_t)i * n + j], L.b[(int64_t)j * k + r], sum);
+        for (int j = part; j < n; j += 8) sum = fma(a.dense[(int64_t)i * n + j], (double)L.b[(int64_t)j * k + r], sum);
       sum += __shfl_xor_sync(0xffffffffu, sum, 4);
       sum += __shfl_xor_sync(0xffffffffu, sum, 2);
       sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      if (ok && part == 0) xs[nl - 1][e] = sum;
+      if (ok && part == 0) xs[nl - 1][e] = (T)sum;
     }
     cluster.sync();
   }
   // ---- up
   for (int l = nl - 2; l >= 0; l--) {
-    const TailLevel& L = a.L[l];
-    const double* xc = xs[l + 1];
+    const TailLevel<T>& L = a.L[l];
+    const T* xc = xs[l + 1];
     for (int64_t e = ctid; e < L.n * k; e += nthreads) {
       const int64_t i = e / k;
       const int r = (int)(e - i * k);
       const int32_t ag = L.agg[i];
-      if (ag >= 0 && L.dinv[i] != 0.0) xs[l][e] = fma(a.alpha, xc[(int64_t)ag * k + r], xs[l][e]);
+      if (ag >= 0 && L.dinv[i] != (T)0) xs[l][e] = fma(a.alpha, xc[(int64_t)ag * k + r], xs[l][e]);
     }
     cluster.sync();
     for (int sw = 0; sw < a.sweeps; sw++) {
-      tail_smooth(L, xs[l], ts[l], k, 0, ctid, nthreads);
-      double* tmp = xs[l]; xs[l] = ts[l]; ts[l] = tmp;
+      tail_smooth<T>(L, xs[l], ts[l], k, 0, ctid, nthreads);
+      T* tmp = xs[l]; xs[l] = ts[l]; ts[l] = tmp;
       cluster.sync();
     }
   }
@@ -499,27 +520,39 @@ int kp_of(int k) {
   return kp;
 }
 
-}  // namespace
-
-void spmm_smooth(Ctx* c, const int64_t* rowptr, const int32_t* col, const double* val, const double* dinv, const double* B,
-                 const double* X, double* OUT, int k, int64_t n, double omega, int mode) {
+template <typename T, typename TBt, typename TOt>
+void smooth_t(Ctx* c, const int64_t* rowptr, const int32_t* col, const T* val, const T* dinv, const TBt* B, const T* X, TOt* OUT, int k,
+              int64_t n, double omega_d, int mode) {
   cudaStream_t st = c->stream;
+  const T omega = (T)omega_d;
   auto grid_of = [&](int G) {
     const int64_t want = (n + (TB / G) - 1) / (TB / G);
     return (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->num_sms * 8));
   };
   if (k & 1) {  // odd stride (only k == 1 in practice): one right-hand side per lane
     const int kp = kp_of(k);
-    if (kp == 1) k_smooth<8, 1, 1><<<grid_of(8), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
-    else if (kp <= 8) k_smooth<8, 8, 1><<<grid_of(8), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
-    else k_smooth<32, 32, 1><<<grid_of(32), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
-  } else if (k <= 2) k_smooth<4, 1, 2><<<grid_of(4), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
-  else if (k <= 4) k_smooth<4, 2, 2><<<grid_of(4), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
-  else if (k <= 8) k_smooth<4, 4, 2><<<grid_of(4), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
-  else if (k <= 16) k_smooth<8, 8, 2><<<grid_of(8), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
-  else k_smooth<16, 16, 2><<<grid_of(16), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
+    if (kp == 1) k_smooth<8, 1, 1, T, TBt, TOt><<<grid_of(8), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
+    else if (kp <= 8) k_smooth<8, 8, 1, T, TBt, TOt><<<grid_of(8), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
+    else k_smooth<32, 32, 1, T, TBt, TOt><<<grid_of(32), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
+  } else if (k <= 2) k_smooth<4, 1, 2, T, TBt, TOt><<<grid_of(4), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
+  else if (k <= 4) k_smooth<4, 2, 2, T, TBt, TOt><<<grid_of(4), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
+  else if (k <= 8) {
+    // 8 lanes per row = two entries of the row in flight per step (rows of the vertex block have ~15 entries: 2 steps instead
+    // of 4 dependent load -> gather rounds; the sweeps are latency-bound, profiles/r02_notes.md)
+    if (c->amg_lanes8) k_smooth<8, 4, 2, T, TBt, TOt><<<grid_of(8), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
+    else k_smooth<4, 4, 2, T, TBt, TOt><<<grid_of(4), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
+  }
+  else if (k <= 16) k_smooth<8, 8, 2, T, TBt, TOt><<<grid_of(8), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
+  else k_smooth<16, 16, 2, T, TBt, TOt><<<grid_of(16), TB, 0, st>>>(rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
   c->launches++;
   CK(cudaGetLastError());
+}
+
+}  // namespace
+
+void spmm_smooth(Ctx* c, const int64_t* rowptr, const int32_t* col, const double* val, const double* dinv, const double* B,
+                 const double* X, double* OUT, int k, int64_t n, double omega, int mode) {
+  smooth_t<double, double, double>(c, rowptr, col, val, dinv, B, X, OUT, k, n, omega, mode);
 }
 
 void amg_release(Ctx* c) {
@@ -527,6 +560,7 @@ void amg_release(Ctx* c) {
   for (auto& L : c->amg) {
     L.rowptr.release(s); L.col.release(s); L.val.release(s); L.dinv.release(s); L.diag.release(s); L.agg.release(s);
     L.members.release(s); L.aggptr.release(s); L.b.release(s); L.x.release(s); L.t.release(s);
+    L.valf.release(s); L.dinvf.release(s); L.bf.release(s); L.xf.release(s); L.tf.release(s);
   }
   c->amg.clear();
   for (auto& T : c->amg_tmp) { T.rowptr.release(s); T.col.release(s); T.val.release(s); T.diag.release(s); }
@@ -708,7 +742,14 @@ void amg_build_hierarchy(Ctx* c) {
     LAUNCH(c, k_level_dinv, grid_for(nc, TB), TB, 0, C.rowptr.p, C.col.p, C.val.p, (const uint8_t*)nullptr, nc, C.dinv.p, C.diag.p);
   }
   c->amg_nlev = nlev;
-  for (int l = 0; l < nlev; l++) c->amg[l].omega = c->amg_omega_scale;  // l1-Jacobi: any weight <= 1 keeps the cycle SPD
+  for (int l = 0; l < nlev; l++) c->amg[l].omega = c->amg_omega_scale;
+  if (c->amg_fp32)
+    for (int l = 0; l < nlev; l++) {  // fp32 copies for the mixed-precision cycle
+      Ctx::AmgLevel& L = c->amg[l];
+      L.valf.ensure(L.nnz, st); L.dinvf.ensure(L.n, st);
+      LAUNCH(c, k_to_float, grid_for(L.nnz, TB), TB, 0, L.val.p, L.valf.p, L.nnz);
+      LAUNCH(c, k_to_float, grid_for(L.n, TB), TB, 0, L.dinv.p, L.dinvf.p, L.n);
+    }  // l1-Jacobi: any weight <= 1 keeps the cycle SPD
   // ---- dense inverse of the coarsest level
   {
     Ctx::AmgLevel& L = c->amg[nlev - 1];
@@ -748,57 +789,84 @@ void amg_setup(Ctx* c) {
 }
 // work blocks of every level for k right-hand sides (grow-only; must be called before a CUDA-graph capture of amg_apply)
 void amg_prepare(Ctx* c, int k) {
+  cudaStream_t st = c->stream;
   for (int l = 0; l < c->amg_nlev; l++) {
     Ctx::AmgLevel& L = c->amg[l];
-    L.b.ensure(L.n * k, c->stream); L.x.ensure(L.n * k, c->stream); L.t.ensure(L.n * k, c->stream);
+    if (c->amg_fp32) {
+      L.bf.ensure(L.n * k, st); L.xf.ensure(L.n * k, st); L.tf.ensure(L.n * k, st);
+    } else {
+      L.b.ensure(L.n * k, st); L.x.ensure(L.n * k, st); L.t.ensure(L.n * k, st);
+    }
   }
   c->amg_nrhs = k;
 }
 
-// z_vert = V-cycle(r_vert) on the leading nv rows of the ndof x k blocks R, Z of the PCG.
-void amg_apply(Ctx* c, const double* R, double* Z, int k) {
+namespace {
+
+// per-level storage of the cycle in precision T
+template <typename T> struct Lv;
+template <> struct Lv<double> {
+  static const double* val(Ctx::AmgLevel& L) { return L.val.p; }
+  static const double* dinv(Ctx::AmgLevel& L) { return L.dinv.p; }
+  static double*& b(Ctx::AmgLevel& L) { return L.b.p; }
+  static double*& x(Ctx::AmgLevel& L) { return L.x.p; }
+  static double*& t(Ctx::AmgLevel& L) { return L.t.p; }
+};
+template <> struct Lv<float> {
+  static const float* val(Ctx::AmgLevel& L) { return L.valf.p; }
+  static const float* dinv(Ctx::AmgLevel& L) { return L.dinvf.p; }
+  static float*& b(Ctx::AmgLevel& L) { return L.bf.p; }
+  static float*& x(Ctx::AmgLevel& L) { return L.xf.p; }
+  static float*& t(Ctx::AmgLevel& L) { return L.tf.p; }
+};
+
+// The V-cycle with the level storage in T.  Level 0 reads its right-hand side from the PCG's fp64 block R and its last sweep
+// writes the fp64 block Z: with T = float every conversion is fused into a sweep.  Levels [lt, nl) run inside the fused
+// tail kernel (lt == nl: per-level launches all the way down and the dense coarsest solve as its own launch).
+template <typename T>
+void vcycle(Ctx* c, const double* R, double* Z, int k, int lt) {
   cudaStream_t st = c->stream;
-  const double alpha = c->amg_alpha;
+  const T alpha = (T)c->amg_alpha;
   const int sweeps = c->amg_sweeps;
   const int nl = c->amg_nlev;
-  amg_prepare(c, k);
-  // levels [lt, nl) go into the fused tail kernel: every level below TAIL_ROWS rows, but never level 0 (its right-hand
-  // side / result are the PCG's blocks) and only for column-pair strides the kernel is written for
-  int lt = nl;
-  if (c->amg_fused_tail && (k & 1) == 0 && k <= 8 && nl >= 2) {
-    lt = nl - 1;
-    while (lt > 1 && c->amg[lt - 1].n <= c->amg_tail_rows) lt--;
-    if (nl - lt < 2) lt = nl;  // the coarsest level alone: nothing to fuse
-  }
   auto down = [&](int l) {
     Ctx::AmgLevel& L = c->amg[l];
-    const double* b = (l == 0) ? R : L.b.p;
     const double omega = L.omega;
-    LAUNCH(c, k_jacobi0, grid_for(L.n * k, TB), TB, 0, L.dinv.p, b, L.x.p, k, L.n, omega);
-    for (int s = 1; s < sweeps; s++) {
-      spmm_smooth(c, L.rowptr.p, L.col.p, L.val.p, L.dinv.p, b, L.x.p, L.t.p, k, L.n, omega, 0);
-      std::swap(L.x.p, L.t.p);
+    if (l == 0) {
+      LAUNCH(c, (k_jacobi0<T, double>), grid_for(L.n * k, TB), TB, 0, Lv<T>::dinv(L), R, Lv<T>::x(L), k, L.n, (T)omega);
+    } else {
+      LAUNCH(c, (k_jacobi0<T, T>), grid_for(L.n * k, TB), TB, 0, Lv<T>::dinv(L), (const T*)Lv<T>::b(L), Lv<T>::x(L), k, L.n, (T)omega);
     }
-    spmm_smooth(c, L.rowptr.p, L.col.p, L.val.p, L.dinv.p, b, L.x.p, L.t.p, k, L.n, omega, 1);  // t = b - A x
+    for (int s = 1; s < sweeps; s++) {
+      if (l == 0) smooth_t<T, double, T>(c, L.rowptr.p, L.col.p, Lv<T>::val(L), Lv<T>::dinv(L), R, Lv<T>::x(L), Lv<T>::t(L), k, L.n, omega, 0);
+      else smooth_t<T, T, T>(c, L.rowptr.p, L.col.p, Lv<T>::val(L), Lv<T>::dinv(L), (const T*)Lv<T>::b(L), Lv<T>::x(L), Lv<T>::t(L), k, L.n, omega, 0);
+      std::swap(Lv<T>::x(L), Lv<T>::t(L));
+    }
+    // t = b - A x
+    if (l == 0) smooth_t<T, double, T>(c, L.rowptr.p, L.col.p, Lv<T>::val(L), Lv<T>::dinv(L), R, Lv<T>::x(L), Lv<T>::t(L), k, L.n, omega, 1);
+    else smooth_t<T, T, T>(c, L.rowptr.p, L.col.p, Lv<T>::val(L), Lv<T>::dinv(L), (const T*)Lv<T>::b(L), Lv<T>::x(L), Lv<T>::t(L), k, L.n, omega, 1);
     Ctx::AmgLevel& C = c->amg[l + 1];
-    LAUNCH(c, k_restrict, grid_for(C.n * k, TB), TB, 0, L.aggptr.p, L.members.p, L.t.p, C.b.p, k, C.n);
+    LAUNCH(c, k_restrict<T>, grid_for(C.n * k, TB), TB, 0, L.aggptr.p, L.members.p, (const T*)Lv<T>::t(L), Lv<T>::b(C), k, C.n);
   };
   auto up = [&](int l) {
     Ctx::AmgLevel& L = c->amg[l];
     Ctx::AmgLevel& C = c->amg[l + 1];
-    const double* b = (l == 0) ? R : L.b.p;
     const double omega = L.omega;
-    LAUNCH(c, k_prolong, grid_for(L.n * k, TB), TB, 0, L.agg.p, L.dinv.p, C.x.p, L.x.p, k, L.n, alpha);
+    LAUNCH(c, k_prolong<T>, grid_for(L.n * k, TB), TB, 0, L.agg.p, Lv<T>::dinv(L), (const T*)Lv<T>::x(C), Lv<T>::x(L), k, L.n, alpha);
     for (int s = 0; s < sweeps; s++) {
-      double* out = (l == 0 && s == sweeps - 1) ? Z : L.t.p;
-      spmm_smooth(c, L.rowptr.p, L.col.p, L.val.p, L.dinv.p, b, L.x.p, out, k, L.n, omega, 0);
-      if (out == L.t.p) std::swap(L.x.p, L.t.p);
+      if (l == 0 && s == sweeps - 1) {
+        smooth_t<T, double, double>(c, L.rowptr.p, L.col.p, Lv<T>::val(L), Lv<T>::dinv(L), R, Lv<T>::x(L), Z, k, L.n, omega, 0);
+      } else {
+        if (l == 0) smooth_t<T, double, T>(c, L.rowptr.p, L.col.p, Lv<T>::val(L), Lv<T>::dinv(L), R, Lv<T>::x(L), Lv<T>::t(L), k, L.n, omega, 0);
+        else smooth_t<T, T, T>(c, L.rowptr.p, L.col.p, Lv<T>::val(L), Lv<T>::dinv(L), (const T*)Lv<T>::b(L), Lv<T>::x(L), Lv<T>::t(L), k, L.n, omega, 0);
+        std::swap(Lv<T>::x(L), Lv<T>::t(L));
+      }
     }
   };
   const int top = std::min(lt, nl - 1);  // per-level launches for the levels [0, top)
   for (int l = 0; l < top; l++) down(l);
   if (lt < nl) {
-    TailArgs a;
+    TailArgs<T> a;
     memset(&a, 0, sizeof a);
     a.nl = nl - lt;
     a.dense = c->amg_dense.p;
@@ -807,24 +875,45 @@ void amg_apply(Ctx* c, const double* R, double* Z, int k) {
     a.alpha = alpha;
     for (int l = lt; l < nl; l++) {
       Ctx::AmgLevel& L = c->amg[l];
-      TailLevel& T = a.L[l - lt];
-      T.rowptr = L.rowptr.p; T.col = L.col.p; T.val = L.val.p; T.dinv = L.dinv.p;
-      T.agg = L.agg.p; T.aggptr = L.aggptr.p; T.members = L.members.p;
-      T.b = L.b.p; T.x = L.x.p; T.t = L.t.p; T.n = L.n; T.omega = L.omega;
+      TailLevel<T>& Tl = a.L[l - lt];
+      Tl.rowptr = L.rowptr.p; Tl.col = L.col.p; Tl.val = Lv<T>::val(L); Tl.dinv = Lv<T>::dinv(L);
+      Tl.agg = L.agg.p; Tl.aggptr = L.aggptr.p; Tl.members = L.members.p;
+      Tl.b = Lv<T>::b(L); Tl.x = Lv<T>::x(L); Tl.t = Lv<T>::t(L); Tl.n = L.n; Tl.omega = (T)L.omega;
     }
-    k_vcycle_tail<<<TAIL_CTAS, TAIL_THREADS, 0, st>>>(a);
+    k_vcycle_tail<T><<<TAIL_CTAS, TAIL_THREADS, 0, st>>>(a);
     c->launches++;
     CK(cudaGetLastError());
     // mirror the kernel's pointer swaps: the result of a non-coarsest tail level ends up where its t block was after an
     // odd number of swaps
     for (int l = lt; l < nl - 1; l++)
-      if (((sweeps - 1) + sweeps) & 1) std::swap(c->amg[l].x.p, c->amg[l].t.p);
+      if (((sweeps - 1) + sweeps) & 1) std::swap(Lv<T>::x(c->amg[l]), Lv<T>::t(c->amg[l]));
   } else {  // coarsest: dense inverse
     Ctx::AmgLevel& L = c->amg[nl - 1];
-    const double* b = (nl == 1) ? R : L.b.p;
-    double* x = (nl == 1) ? Z : L.x.p;
-    LAUNCH(c, k_dense_apply, grid_for(L.n * k * 8, 128), 128, 0, (int)L.n, c->amg_dense.p, b, x, k);
+    LAUNCH(c, k_dense_apply_t<T>, grid_for(L.n * k * 8, 128), 128, 0, (int)L.n, c->amg_dense.p, (const T*)Lv<T>::b(L), Lv<T>::x(L), k);
   }
   for (int l = top - 1; l >= 0; l--) up(l);
+}
+
+}  // namespace
+
+// z_vert = V-cycle(r_vert) on the leading nv rows of the ndof x k blocks R, Z of the PCG.
+void amg_apply(Ctx* c, const double* R, double* Z, int k) {
+  const int nl = c->amg_nlev;
+  amg_prepare(c, k);
+  if (nl == 1) {  // the vertex block itself is small enough for the dense inverse
+    Ctx::AmgLevel& L = c->amg[0];
+    LAUNCH(c, k_dense_apply_t<double>, grid_for(L.n * k * 8, 128), 128, 0, (int)L.n, c->amg_dense.p, R, Z, k);
+    return;
+  }
+  // levels [lt, nl) go into the fused tail kernel: every level below amg_tail_rows rows, but never level 0 (its right-hand
+  // side / result are the PCG's blocks) and only for the column-pair strides the kernel is written for
+  int lt = nl;
+  if (c->amg_fused_tail && (k & 1) == 0 && k <= 8 && nl >= 2) {
+    lt = nl - 1;
+    while (lt > 1 && c->amg[lt - 1].n <= c->amg_tail_rows) lt--;
+    if (nl - lt < 2) lt = nl;  // the coarsest level alone: nothing to fuse
+  }
+  if (c->amg_fp32) vcycle<float>(c, R, Z, k, lt);
+  else vcycle<double>(c, R, Z, k, lt);
   // the high-order rows (z = D^-1 r) are handled inside the PCG vector kernels (k_init / k_update_r / k_update_px, tail_from = nv)
 }

@@ -403,6 +403,7 @@ int remo_set_option(void* vctx, const char* name, double value) {
     const std::string n(name);
     if (n == "amg_alpha") c->amg_alpha = value;
     else if (n == "amg_sweeps") c->amg_sweeps = std::max(1, (int)value);
+    else if (n == "ebe_check") { c->ebe_check = value != 0.0 ? 1 : 0; c->have_ebe = false; c->pkind = -1; }
     else if (n == "spmm_ebe") { c->ebe_on = value != 0.0 ? 1 : 0; c->have_ebe = false; c->pkind = -1; }
     else if (n == "amg_omega_scale") { c->amg_omega_scale = value; c->pkind = -1; }
     else if (n == "amg_agg") { c->amg_agg = value != 0.0 ? 1 : 0; c->pkind = -1; }
@@ -410,6 +411,8 @@ int remo_set_option(void* vctx, const char* name, double value) {
     else if (n == "amg_rounds") { c->amg_rounds = std::min(32, std::max(1, (int)value)); c->pkind = -1; }
     else if (n == "lazy_matrix") c->lazy_matrix = value != 0.0;
     else if (n == "amg_fused_tail") c->amg_fused_tail = value != 0.0 ? 1 : 0;
+    else if (n == "amg_lanes8") c->amg_lanes8 = value != 0.0 ? 1 : 0;
+    else if (n == "amg_fp32") { c->amg_fp32 = value != 0.0 ? 1 : 0; c->pkind = -1; }
     else if (n == "amg_tail_rows") c->amg_tail_rows = (int64_t)value;
     else FAIL(REMO_ERR_ARG, "remo_set_option: unknown option '%s'", name);
     return REMO_OK;

@@ -130,6 +130,7 @@ struct Ctx {
   int ebe_fast8 = 0;  // every dof piece has <= 8 entries and every batch <= 1024 of them: register tables in the kernel
   int ebe_occ[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // resident CTAs per SM by right-hand-side count
   bool have_ebe = false;
+  int ebe_check = 0;  // remo_set_option("ebe_check", 1): validate the batch tables after every build (ebe.cu k_ebe_check)
   int ebe_on = -1;  // remo_set_option("spmm_ebe"): 0 / 1, -1 = the REMO_SPMM_EBE environment default (on)
 
   // ---- numeric
@@ -152,6 +153,7 @@ struct Ctx {
     DBuf<int32_t> aggptr;     // nc + 1: first entry of every aggregate in members
     double omega = 1.0;       // weight of the l1-Jacobi sweeps
     DBuf<double> b, x, t;     // n x nrhs work blocks (level 0 uses R / Z of the PCG directly for b / x)
+    DBuf<float> valf, dinvf, bf, xf, tf;  // mixed-precision cycle (amg_fp32): fp32 copies of the matrix / weights, fp32 work blocks
   };
   std::vector<AmgLevel> amg;
   struct AmgTmp {  // Galerkin products between the passes of one level's pairwise aggregation
@@ -168,6 +170,8 @@ struct Ctx {
   int64_t amg_tail_rows = 20000;
   double amg_alpha = 1.5, amg_omega_scale = 1.0;  // coarse-correction scaling, weight of the l1-Jacobi sweeps (<= 1)
   int amg_sweeps = 1;                              // pre = post smoothing sweeps
+  int amg_lanes8 = 1;                              // k_smooth<8,4,2> instead of <4,4,2> for 5..8 right-hand sides
+  int amg_fp32 = 1;                                // 1: the V-cycle runs in fp32 (fp64 PCG around it), amg.cu vcycle_levels<float>
   int amg_gamma = 1;                               // cycle index: 1 = V, 2 = W
   DBuf<double> amg_dense;     // inverse of the coarsest matrix (n x n)
   int amg_nrhs = 0;

@@ -524,6 +524,54 @@ __global__ void __launch_bounds__(TPB, 3) k_spmm_ebe(int nb, const int64_t* __re
   }
 }
 
+// Table validator (remo_set_option("ebe_check", 1); compute-sanitizer is not available on every pool, so the bounds the
+// product kernel relies on are asserted here, once per matrix): per batch U <= umax, every dof number < ndof, every slot's
+// staged row < U, the 2560 scratch positions are a permutation of 0..2559 (no two results of a pass land on the same word),
+// every real entry sits on one of the first ucnt[row] diagonals of its row, and the entry counts add up.
+__global__ void __launch_bounds__(TPB) k_ebe_check(int64_t nt, int64_t ndof, int umax, const int64_t* __restrict__ uoff,
+                                                   const int32_t* __restrict__ udof, const uint16_t* __restrict__ lidx,
+                                                   const uint16_t* __restrict__ lpos, const uint16_t* __restrict__ ucnt,
+                                                   const uint16_t* __restrict__ jdp, int* __restrict__ err) {
+  __shared__ uint32_t seen[(TPB * NLD + 31) / 32];
+  __shared__ int cnt_sum;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int64_t u0 = uoff[b];
+  const int U = (int)(uoff[b + 1] - u0);
+  for (int i = tid; i < (TPB * NLD + 31) / 32; i += TPB) seen[i] = 0;
+  if (tid == 0) cnt_sum = 0;
+  __syncthreads();
+  int bad = 0;
+  if (tid == 0 && (U > umax || U < 1)) bad++;
+  int mine = 0;
+  for (int u = tid; u < U; u += TPB) {
+    if ((int64_t)(udof[u0 + u] & 0x7fffffff) >= ndof) bad++;
+    const int n = ucnt[u0 + u];
+    if (n < 1 || n > TPB) bad++;
+    mine += n;
+  }
+  atomicAdd(&cnt_sum, mine);
+  const int64_t left = nt - (int64_t)b * TPB;
+  const bool real = tid < left;
+  const uint16_t* jd = jdp + (int64_t)b * EBE_JD;
+  for (int k = 0; k < NLD; k++) {
+    const int64_t o = ((int64_t)b * NLD + k) * TPB + tid;
+    const int row = lidx[o], pos = lpos[o];
+    if (pos >= TPB * NLD) { bad++; continue; }
+    if (atomicOr(&seen[pos >> 5], 1u << (pos & 31)) & (1u << (pos & 31))) bad++;
+    if (real) {
+      if (row >= U) { bad++; continue; }
+      const int n = ucnt[u0 + row];
+      bool found = false;
+      for (int i = 0; i < n && i < EBE_JD; i++) found |= (int)jd[i] + row == pos;
+      if (!found) bad++;
+    }
+  }
+  __syncthreads();
+  const int nvalid = (int)((left < TPB ? left : TPB) * NLD);
+  if (tid == 0 && cnt_sum != nvalid) bad++;
+  if (bad) atomicAdd(err, bad);
+}
+
 size_t ebe_smem(int umax, int nr) {
   const int xst = nr | 1;
   return (size_t)umax * xst * 8 + (size_t)NLD * TPB * 8 + (size_t)umax * 4 + (size_t)(umax + EBE_JD) * 2;
@@ -606,6 +654,15 @@ void ebe_build(Ctx* c) {
     // the kernel keeps byte offsets into xs as 16-bit numbers
     if (sm <= (size_t)dev_max && (size_t)umax * (nr | 1) * 8 < 65536) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_ebe, TPB, sm));
     c->ebe_occ[nr] = occ;  // 0: a batch does not fit (degenerate mesh) -> the SELL / CSR kernels take over
+  }
+  if (c->ebe_check) {
+    int* err_d = scratch<int>(c, 6, 1);
+    int err = 0;
+    CK(cudaMemsetAsync(err_d, 0, sizeof(int), st));
+    LAUNCH(c, k_ebe_check, (unsigned)nb, TPB, 0, nt, c->ndof, umax, c->ebe_uoff.p, c->ebe_udof.p, c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_ucnt.p, c->ebe_jd.p, err_d);
+    CK(cudaMemcpyAsync(&err, err_d, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (err) FAIL(REMO_ERR_STATE, "ebe_check: %d violations in the batch tables", err);
   }
   c->have_ebe = true;
 }

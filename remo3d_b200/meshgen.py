@@ -96,11 +96,16 @@ def boundary_facets(elems, return_owner=False):
 # graded half-ball
 # ----------------------------------------------------------------------------------------------
 class SizeField:
-    """h(x) = min( h_electrode + g*dist(electrodes),  h_axis + g*dist(tool segment),  h_max )."""
+    """h(x) = min( h_electrode + g*dist(electrodes),  h_axis + g*dist(tool segment),  h_max
+                   [, h_borehole + g*max(0, rho - r_strip)  -- the borehole column resolved along the WHOLE axis, as a mesher
+                      that fragments the domain by the borehole cylinder does (`gmsh_functions.py:576-591`)] )."""
 
-    def __init__(self, electrodes_z, h_electrode, h_axis, h_max, grading):
+    def __init__(self, electrodes_z, h_electrode, h_axis, h_max, grading, h_borehole=None, r_strip=0.0, g_borehole=0.6,
+                 borehole_window=10.0, g_window=0.08):
         self.ez = np.asarray(sorted(electrodes_z), dtype=float)
         self.h_e, self.h_a, self.h_max, self.g = h_electrode, h_axis, h_max, grading
+        # borehole term: h_b + g_b * max(0, rho - r_strip) + g_w * max(0, axial distance to the tool - window)
+        self.h_b, self.r_strip, self.g_b, self.win, self.g_w = h_borehole, float(r_strip), float(g_borehole), float(borehole_window), float(g_window)
         self.z_lo, self.z_hi = self.ez[0], self.ez[-1]
 
     def __call__(self, p):
@@ -115,7 +120,19 @@ class SizeField:
         d_e = np.sqrt(rho2 + dz ** 2)
         zc = np.clip(z, self.z_lo, self.z_hi)
         d_a = np.sqrt(rho2 + (z - zc) ** 2)
-        return np.minimum(np.minimum(self.h_e + self.g * d_e, self.h_a + self.g * d_a), self.h_max)
+        h = np.minimum(np.minimum(self.h_e + self.g * d_e, self.h_a + self.g * d_a), self.h_max)
+        if self.h_b is not None:
+            far = np.maximum(0.0, np.abs(z - zc) - self.win)
+            h = np.minimum(h, self.h_b + self.g_b * np.maximum(0.0, np.sqrt(rho2) - self.r_strip) + self.g_w * far)
+        return h
+
+    def reach_b(self, s):
+        """Radius around the axis inside which the borehole term asks for h < 2 s (<= 0: nowhere)."""
+        return -1.0 if self.h_b is None else (2 * s - self.h_b) / self.g_b + self.r_strip
+
+    def zreach_b(self, s):
+        """Axial distance beyond the tool segment up to which the borehole term asks for h < 2 s."""
+        return self.win + (2 * s - self.h_b) / self.g_w
 
 
 def _axis_points(size, radius):
@@ -142,11 +159,14 @@ def _bcc_level_points(level, s, size, radius, rng, jitter, half):
     else:
         reach_e = (2 * s - size.h_e) / size.g
         reach_a = (2 * s - size.h_a) / size.g
-    if reach_e <= 0 and reach_a <= 0:
+    reach_b = size.reach_b(s) if level > 0 else -1.0
+    if reach_e <= 0 and reach_a <= 0 and reach_b <= 0:
         return np.zeros((0, 3))
-    reach = min(max(reach_e, reach_a, 0.0) + 2 * s, radius)
+    reach = min(max(reach_e, reach_a, reach_b, 0.0) + 2 * s, radius)
     zlo = max(size.z_lo - reach, -radius)
     zhi = min(size.z_hi + reach, radius)
+    if reach_b > 0:  # the borehole column is resolved well beyond the tool
+        zlo, zhi = max(min(zlo, size.z_lo - size.zreach_b(s)), -radius), min(max(zhi, size.z_hi + size.zreach_b(s)), radius)
     nxy = int(np.ceil(reach / u))
     ix = np.arange(-nxy, nxy + 1)
     iy = np.arange(0 if half else -nxy, nxy + 1)
@@ -184,12 +204,14 @@ def _plane_level_points(level, s, size, radius, rng, jitter):
     if level == 0:
         reach = radius
     else:
-        r = max((2 * s - size.h_e) / size.g, (2 * s - size.h_a) / size.g)
+        r = max((2 * s - size.h_e) / size.g, (2 * s - size.h_a) / size.g, size.reach_b(s))
         if r <= 0:
             return np.zeros((0, 3))
         reach = min(r + 2 * s, radius)
     zlo = max(size.z_lo - reach, -radius)
     zhi = min(size.z_hi + reach, radius)
+    if level > 0 and size.reach_b(s) > 0:
+        zlo, zhi = max(min(zlo, size.z_lo - size.zreach_b(s)), -radius), min(max(zhi, size.z_hi + size.zreach_b(s)), radius)
     nx = int(np.ceil(reach / u))
     ix = np.arange(-nx, nx + 1)
     iz = np.arange(int(np.floor(zlo / u)), int(np.ceil(zhi / u)) + 1)
@@ -227,16 +249,82 @@ def _sphere_points(radius, h, half):
     return np.concatenate([p, rim])
 
 
+class Interfaces:
+    """Material interfaces of a layered formation around a borehole, in the mesh frame (`gmsh_functions.py:576-624`: the
+    reference fragments the half-ball by the borehole cylinder, the layer planes and the invasion cylinders, so its
+    interfaces are mesh faces).  Here the point cloud is made to carry them: every lattice point closer than `frac` of the
+    local size to an interface is PROJECTED onto it (radially onto a cylinder, vertically onto a dipping plane -- both keep
+    a symmetry-plane point on y = 0), near-duplicates among the projected points are dropped, and the Delaunay tets then have
+    the surfaces as (almost all) faces; the per-tet material still comes from the centroid.
+
+      wall      : (z, r) arrays -- borehole radius along the axis (caliper), or a scalar
+      tops      : ascending interface depths on the axis between consecutive layers
+      dip_rad   : layer planes z = top_i + tan(dip) x
+      invasion  : per layer (len(tops) + 1) flushed-zone radius or None"""
+
+    def __init__(self, wall, tops, dip_rad=0.0, invasion=None):
+        self.wall = wall
+        self.tops = np.asarray(tops, dtype=float)
+        self.tan = float(np.tan(dip_rad))
+        self.cos = float(np.cos(dip_rad))
+        nl = self.tops.shape[0] + 1
+        inv = [None] * nl if invasion is None else list(invasion)
+        self.inv = np.array([np.nan if (v is None or v != v) else float(v) for v in inv])
+
+    def wall_radius(self, z):
+        return np.full(z.shape, float(self.wall)) if np.isscalar(self.wall) else np.interp(z, self.wall[0], self.wall[1])
+
+    def snap(self, pts, h, movable, frac=0.5):
+        """-> (points, snapped mask).  `movable`: points that may move at all (not the axis, not the sphere)."""
+        rho = np.hypot(pts[:, 0], pts[:, 1])
+        z = pts[:, 2]
+        best = np.full(pts.shape[0], np.inf)
+        kind = np.zeros(pts.shape[0], np.int8)  # 1 = radial to radius `target`, 2 = vertical to depth `target`
+        target = np.zeros(pts.shape[0])
+        # borehole wall
+        rb = self.wall_radius(z)
+        d = np.abs(rho - rb)
+        best, kind, target = d.copy(), np.ones(pts.shape[0], np.int8), rb.copy()
+        # layer planes (only outside the borehole: inside it is all mud)
+        zeff = z - self.tan * pts[:, 0]
+        if self.tops.size:
+            j = np.clip(np.searchsorted(self.tops, zeff), 0, self.tops.size)
+            for cand in (np.clip(j - 1, 0, self.tops.size - 1), np.clip(j, 0, self.tops.size - 1)):
+                dz = np.abs(zeff - self.tops[cand]) * self.cos
+                use = (dz < best) & (rho > rb - frac * h)
+                best = np.where(use, dz, best)
+                kind = np.where(use, 2, kind).astype(np.int8)
+                target = np.where(use, self.tops[cand] + self.tan * pts[:, 0], target)
+        # invasion cylinders of the layer the point is in
+        layer = np.searchsorted(self.tops, zeff) if self.tops.size else np.zeros(pts.shape[0], int)
+        ri = self.inv[layer]
+        di = np.abs(rho - ri)
+        use = np.isfinite(ri) & (di < best)
+        best = np.where(use, di, best)
+        kind = np.where(use, 1, kind).astype(np.int8)
+        target = np.where(use, ri, target)
+        go = movable & (best < frac * h) & (rho > 1e-12)
+        out = pts.copy()
+        rad = go & (kind == 1)
+        scale = np.where(rad, target / np.where(rho > 0, rho, 1.0), 1.0)
+        out[:, 0] *= scale
+        out[:, 1] *= scale
+        ver = go & (kind == 2)
+        out[ver, 2] = target[ver]
+        return out, go
+
+
 def half_ball_points(radius, electrodes_z, h_electrode=0.02, h_axis=0.1, h_max=None, grading=0.35, seed=0, half=True,
-                     jitter=0.08):
+                     jitter=0.08, interfaces=None, snap_frac=0.5, h_borehole=None, r_strip=0.0, g_borehole=0.6, borehole_window=10.0,
+                     g_window=0.08):
     """Graded point cloud; returns (points, n_axis) with the axis points first (sorted by z)."""
     rng = np.random.default_rng(seed)
     h_max = h_max or radius / 8.0
-    size = SizeField(electrodes_z, h_electrode, h_axis, h_max, grading)
+    size = SizeField(electrodes_z, h_electrode, h_axis, h_max, grading, h_borehole, r_strip, g_borehole, borehole_window, g_window)
     axis_z = _axis_points(size, radius)
     axis = np.stack([np.zeros_like(axis_z), np.zeros_like(axis_z), axis_z], axis=1)
     nlev = int(np.ceil(np.log2(h_max / min(h_electrode, h_axis)))) + 1
-    vol, pla = [], []
+    vol, pla = [], []  # (2D mesher: same structure, meshgen2d.half_disc_mesh)
     for level in range(nlev):
         s = h_max / 2 ** level
         p = _bcc_level_points(level, s, size, radius, rng, jitter, half)
@@ -257,6 +345,30 @@ def half_ball_points(radius, electrodes_z, h_electrode=0.02, h_axis=0.1, h_max=N
     # exactly cospherical points make one giant degenerate facet of the lifted hull (Qhull crawls):
     # pull them inside by a relative 1e-7 at random; "on the sphere" is tested with 1e-6 below
     sph *= 1.0 - 1e-7 * rng.uniform(0.0, 1.0, size=(sph.shape[0], 1))
+    if interfaces is not None:
+        # carry the material interfaces in the point cloud (class Interfaces): project, then thin out near-duplicates
+        from scipy.spatial import cKDTree
+
+        inner = np.concatenate(pla + vol) if (pla or vol) else np.zeros((0, 3))
+        h = size(inner)
+        inner, snapped = interfaces.snap(inner, h, np.ones(inner.shape[0], bool), snap_frac)
+        # keep clear of the axis chain and of the sphere after the move
+        ok = (np.hypot(inner[:, 0], inner[:, 1]) > 0.6 * h) | ~snapped
+        ok &= (np.linalg.norm(inner, axis=1) < radius - 0.55 * h) | ~snapped
+        inner, snapped, h = inner[ok], snapped[ok], h[ok]
+        if snapped.any():
+            tree = cKDTree(inner)
+            dist, nb = tree.query(inner[snapped], k=2)
+            idx = np.nonzero(snapped)[0]
+            # a projected point that lands within 0.4 h of another point goes (of a pair of projected points the later one)
+            close = dist[:, 1] < 0.4 * h[idx]
+            other = nb[:, 1]
+            drop = close & (~snapped[other] | (other < idx))
+            keep = np.ones(inner.shape[0], bool)
+            keep[idx[drop]] = False
+            inner = inner[keep]
+        parts = [axis, inner, sph]
+        return np.concatenate(parts), axis.shape[0], size
     parts = [axis] + pla + vol + [sph]
     return np.concatenate(parts), axis.shape[0], size
 
@@ -361,6 +473,7 @@ def half_ball_mesh(radius, electrodes_z, material=None, **kw):
     -> 0-based material index per tet (default: all 0)."""
     half = kw.get("half", True)
     pts, n_axis, _ = half_ball_points(radius, electrodes_z, **{k: v for k, v in kw.items() if k not in ("improve", "improve_quality", "improve_mode", "improve_local")})
+    # `interfaces=Interfaces(...)`: points projected onto the material interfaces (see class Interfaces)
     # Morton order with 21 bits per axis (locality of vertex numbers -> locality of CSR columns, at every
     # refinement level: the finest cells here are ~1e-4 of the domain)
     q = np.clip(((pts + radius) / (2 * radius) * (2 ** 21 - 1)).astype(np.uint64), 0, 2 ** 21 - 1)

@@ -158,7 +158,8 @@ class Model:
         the reference's single MPI gather, `remo3d.py:865`), `mesh_options` (mesh sizes; with
         `mesh_generator="gmsh"` a `"msh_path"` entry reads every task's mesh from a Gmsh MSH 2.2 file), `results_log` (a
         JSON-lines file that receives every finished task; with `resume=True` the tasks already in it are not solved
-        again), `share_geometry` (3D: tasks with the same electrode pattern share one triangulation).
+        again), `share_geometry` (3D with `mesh_options={"conforming": False}`: tasks with the same electrode pattern share one
+        triangulation and the material is taken per tet centroid; the default 3D meshes carry the interfaces and are per task).
         Per-task failures (meshing or solving) give NaN log points and an `error` entry in `task_records`."""
         start_time = datetime.datetime.now()
         measurement_depths = np.asarray(measurement_depths, dtype=float)
@@ -221,10 +222,13 @@ class Model:
             mine = set(worker.shard(n_tasks, int(task_shard[0]), int(task_shard[1])))
             todo = [i for i in todo if i in mine]
 
+        mesh_opts_task = dict(mesh_options or {})
+        mesh_opts_task.setdefault("conforming", True)
+
         def job_args(i, geometry=None):
             t = task_list[i]
             return (self.formation_model, borehole_geometry, self.dip_rad, simulation_depths[t[0]], t[1][0], mud_resistivities[t[0]],
-                    domain_radius, mesh_options, geometry, i)
+                    domain_radius, mesh_opts_task, geometry, i)
 
         jobs = queue.Queue(maxsize=2 * len(self._contexts) + 2)
         stop = threading.Event()
@@ -273,7 +277,11 @@ class Model:
         mesh_seconds = 0.0
         try:
             three_d = not np.isclose(self.dip_rad, 0.0)
-            use_shared = three_d and share_geometry and (mesh_options or {}).get("msh_path") is None
+            # 3D meshes carry the material interfaces (`mesh_options["conforming"]`, default True: the reference's Gmsh path
+            # fragments the domain by them, `gmsh_functions.py:576-624`), so they depend on the depth of the batch; with
+            # conforming=False the material is taken per tet centroid and one triangulation serves every task of a pattern
+            conforming = bool((mesh_options or {}).get("conforming", True))
+            use_shared = three_d and share_geometry and not conforming and (mesh_options or {}).get("msh_path") is None
             if use_shared:
                 # one triangulation per electrode pattern, built ahead by the pool (largest groups first); the per-task part
                 # (material of every tet at the task's depth) is cheap and runs here while the GPUs solve

@@ -3,8 +3,9 @@ Examples/Example_01 vs `Examples/Example_01/Output/Results_2024_08_17__18_59_29/
 
 The reference solved 2D axisymmetric Netgen meshes at order 3.  Two runs:
   * the same 2D axisymmetric path here (conforming 2D mesher, order 3): agreement at the reference's mesh-noise level;
-  * the 3D half-ball path with a tiny dip (materials per tet centroid, interfaces not conforming, order 2): agreement
-    at the discretisation level (a couple of per cent).  Depths are chosen inside thick beds."""
+  * the 3D half-ball path with a tiny dip (order 2; the meshes carry the borehole wall, the layer planes and the invasion
+    cylinders, `mesh_options["conforming"]` = the Model default): <= 6e-3 on the CPU oracle with the same meshes, bound 1e-2
+    (round 1, materials per tet centroid: 1.8 %, bound 4e-2).  Depths inside thick beds and next to a bed boundary."""
 import os
 
 import numpy as np
@@ -12,7 +13,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-TOL = 0.04
+TOL = 0.01
 
 
 def test_example01_2d_path_matches_reference_output(golden_dir):
@@ -43,7 +44,7 @@ def test_example01_logs_match_reference_output(golden_dir):
     gold = np.loadtxt(os.path.join(d, "Results_1.txt"), skiprows=2)
     names = open(os.path.join(d, "Results_1.txt")).readline().split()[1:]
     tools = ["A2.0M0.5N", "N0.5M2.0A", "M1.0A0.1B"]
-    depths = np.array([5.5, 6.0, 15.0, 15.5])
+    depths = np.array([5.5, 6.0, 8.3, 15.0, 15.5])
     model = Model.compute_synthetic_logs(tools, depths, os.path.join(d, "Formation.txt"), os.path.join(d, "Borehole.txt"),
                                          dip=0.01, cpu_workers=4, gpu_workers=1, order=2,
                                          mesh_options={"h_electrode": 0.012, "h_axis": 0.035, "grading": 0.28})

@@ -16,6 +16,7 @@ from remo3d_b200 import _cabi  # noqa: E402
 
 def run(name, mesh, sigma, flat, order, precond, opts=()):
     ctx = _cabi.Context(0)
+    ctx.set_option("ebe_check", 1)
     for k, v in opts:
         ctx.set_option(k, v)
     ctx.mesh_set(mesh.dim, mesh.points, mesh.elems, mesh.mat, mesh.bfacets, mesh.dirichlet_flags("dirichlet_boundary"), mesh.axis_vertices())
