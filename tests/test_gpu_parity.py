@@ -206,15 +206,19 @@ def test_aggregation_variants_same_solution(ctx, opts):
     assert its["this"] <= 1.15 * its["morton"] + 2, its
 
 
-def test_fused_tail_of_the_vcycle_is_bit_identical(ctx):
-    """The small levels of the V-cycle run as one cluster kernel (amg.cu k_vcycle_tail); with the per-level launches
-    instead the PCG must take the same iterations and give the same bits (SELL product: deterministic summation order)."""
+@pytest.mark.parametrize("fp32", [0, 1])
+def test_fused_tail_of_the_vcycle_is_bit_identical(ctx, fp32):
+    """The small levels of the V-cycle can run as one cluster kernel (amg.cu k_vcycle_tail<T>, both precisions of the cycle);
+    with the per-level launches of the same lane layout (4 lanes per row) the PCG must take the same iterations and give the
+    same bits (SELL product: deterministic summation order)."""
     mesh, sigma, flat, _ = helpers.ball_case(h_electrode=0.05, h_axis=0.2, grading=0.45)
     _setup(ctx, mesh, 2)
     ctx.assemble(sigma)
     out = {}
     try:
         ctx.set_option("spmm_ebe", 0)
+        ctx.set_option("amg_fp32", fp32)
+        ctx.set_option("amg_lanes8", 0)
         for fused in (1, 0):
             ctx.set_option("amg_fused_tail", fused)
             ctx.set_option("amg_tail_rows", 4000)
@@ -223,13 +227,40 @@ def test_fused_tail_of_the_vcycle_is_bit_identical(ctx):
             it, relres = ctx.solve(rtol=1e-10, maxit=3000)
             assert (relres <= 1e-10).all()
             out[fused] = (it.copy(), np.stack([ctx.solution(r) for r in range(ctx.nrhs)]))
-            print("fused", fused, "iterations", it.tolist(), "levels", ctx.precond_get()[2])
+            print("fp32", fp32, "fused", fused, "iterations", it.tolist(), "levels", ctx.precond_get()[2])
     finally:
         ctx.set_option("spmm_ebe", 1)
         ctx.set_option("amg_fused_tail", 0)
         ctx.set_option("amg_tail_rows", 20000)
+        ctx.set_option("amg_fp32", 1)
+        ctx.set_option("amg_lanes8", 1)
     assert np.array_equal(out[0][0], out[1][0])
     assert np.array_equal(out[0][1], out[1][1])
+
+
+def test_mixed_precision_vcycle_against_the_fp64_cycle(ctx):
+    """`amg_fp32` (default): the V-cycle in fp32 inside the fp64 PCG.  Same solution to 1e-8, iteration counts within 3 of the
+    fp64 cycle, for 1 / 5 right-hand sides and both lane layouts of the sweeps."""
+    mesh, sigma, flat, _ = helpers.ball_case(h_electrode=0.05, h_axis=0.2, grading=0.45)
+    _setup(ctx, mesh, 2)
+    ctx.assemble(sigma)
+    res = {}
+    try:
+        for fp32, lanes8 in ((0, 0), (1, 0), (1, 1), (0, 1)):
+            ctx.set_option("amg_fp32", fp32)
+            ctx.set_option("amg_lanes8", lanes8)
+            ctx.precond_setup("multigrid")
+            ctx.rhs_point_sources(flat["src_ptr"], flat["src_z"], flat["src_fac"])
+            it, relres = ctx.solve(rtol=1e-10, maxit=3000)
+            assert (relres <= 1e-10).all()
+            res[(fp32, lanes8)] = (it.copy(), np.stack([ctx.solution(r) for r in range(ctx.nrhs)]))
+    finally:
+        ctx.set_option("amg_fp32", 1)
+        ctx.set_option("amg_lanes8", 1)
+    it0, u0 = res[(0, 0)]
+    for key, (it, u) in res.items():
+        assert np.abs(it.astype(int) - it0.astype(int)).max() <= 3, (key, it, it0)
+        assert np.abs(u - u0).max() <= 1e-8 * np.abs(u0).max(), key
 
 
 def test_mesh_after_the_sliver_pass_matches_oracle(ctx):
