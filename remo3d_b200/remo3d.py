@@ -218,9 +218,17 @@ class Model:
                 print("{} tasks taken from {}".format(len(done), results_log))
             log_file = open(results_log, "a" if resume else "w")
         todo = [i for i in range(n_tasks) if i not in done]
+        three_d = not np.isclose(self.dip_rad, 0.0)
+        # 3D meshes carry the material interfaces (`mesh_options["conforming"]`, default True: the reference's Gmsh path
+        # fragments the domain by them, `gmsh_functions.py:576-624`), so they depend on the depth of the batch; with
+        # conforming=False the material is taken per tet centroid and one triangulation serves every task of a pattern
+        conforming = bool((mesh_options or {}).get("conforming", True))
+        use_shared = three_d and share_geometry and not conforming and (mesh_options or {}).get("msh_path") is None
         if task_shard is not None:
-            mine = set(worker.shard(n_tasks, int(task_shard[0]), int(task_shard[1])))
-            todo = [i for i in todo if i in mine]
+            keyof = None
+            if use_shared:
+                keyof = {i: model_mesh.geometry_key(self.dip_rad, task_list[i][1][0], domain_radius, mesh_options) for i in todo}
+            todo = worker.shard_tasks(todo, n_tasks, int(task_shard[0]), int(task_shard[1]), keyof)
 
         mesh_opts_task = dict(mesh_options or {})
         mesh_opts_task.setdefault("conforming", True)
@@ -276,12 +284,6 @@ class Model:
         t_mesh0 = datetime.datetime.now().timestamp()
         mesh_seconds = 0.0
         try:
-            three_d = not np.isclose(self.dip_rad, 0.0)
-            # 3D meshes carry the material interfaces (`mesh_options["conforming"]`, default True: the reference's Gmsh path
-            # fragments the domain by them, `gmsh_functions.py:576-624`), so they depend on the depth of the batch; with
-            # conforming=False the material is taken per tet centroid and one triangulation serves every task of a pattern
-            conforming = bool((mesh_options or {}).get("conforming", True))
-            use_shared = three_d and share_geometry and not conforming and (mesh_options or {}).get("msh_path") is None
             if use_shared:
                 # one triangulation per electrode pattern, built ahead by the pool (largest groups first); the per-task part
                 # (material of every tet at the task's depth) is cheap and runs here while the GPUs solve

@@ -85,6 +85,25 @@ def shard(n_tasks, rank, world):
     return list(range(rank, n_tasks, world))
 
 
+def shard_tasks(todo, n_tasks, rank, world, pattern_of=None):
+    """The tasks of `todo` this rank solves.  Default: the interleaved partition of `shard`.  With `pattern_of` (task -> key of
+    the triangulation it shares with other tasks, `model_mesh.geometry_key`) the shards are pattern-aware: tasks ordered by
+    (size of their pattern group, pattern), every rank takes a contiguous slice -- a rank then builds 2-3 of the
+    triangulations instead of every rank building all of them (measured with interleaved shards at N = 8: 42 % GPU busy, the
+    host pools of all ranks triangulating the same 11 patterns)."""
+    if world <= 1:
+        return list(todo)
+    if pattern_of is None:
+        mine = set(shard(n_tasks, rank, world))
+        return [i for i in todo if i in mine]
+    size = {}
+    for i in todo:
+        size[pattern_of[i]] = size.get(pattern_of[i], 0) + 1
+    order = sorted(todo, key=lambda i: (-size[pattern_of[i]], pattern_of[i], i))
+    lo, hi = (len(order) * rank) // world, (len(order) * (rank + 1)) // world
+    return sorted(order[lo:hi])
+
+
 def gather_results(local_triples, world=1):
     """The reference's single final gather (`remo3d.py:865`): every rank contributes its [depth, tool, Ra] triples.
     Uses torch.distributed (gloo or nccl) when a process group is initialised, else returns the local list."""

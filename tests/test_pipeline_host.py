@@ -153,3 +153,20 @@ def test_msh_files_as_task_meshes(tmp_path):
     finally:
         m._contexts = None
         m.shutdown_workers()
+
+
+def test_pattern_aware_shards_partition_the_tasks():
+    """`worker.shard_tasks` with the electrode-pattern key: disjoint, complete, balanced to one task, and every rank touches
+    few patterns (interleaved shards touch all of them)."""
+    rng = np.random.default_rng(0)
+    n = 413
+    pattern = {i: int(p) for i, p in enumerate(rng.choice(11, size=n, p=np.r_[np.full(8, 0.11), np.full(3, 0.04)]))}
+    todo = [i for i in range(n) if i % 17 != 3]  # a resumed run: some tasks already done
+    for world in (2, 4, 8):
+        parts = [worker.shard_tasks(todo, n, r, world, pattern) for r in range(world)]
+        assert sorted(i for p in parts for i in p) == todo
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+        touched = [len({pattern[i] for i in p}) for p in parts]
+        inter = [len({pattern[i] for i in worker.shard_tasks(todo, n, r, world)}) for r in range(world)]
+        assert max(touched) <= 11 // world + 3 and sum(touched) < sum(inter), (world, touched, inter)
+    assert worker.shard_tasks(todo, n, 0, 1, pattern) == todo
