@@ -590,6 +590,53 @@ def run_pipeline(args):
         dist.destroy_process_group()
 
 
+def run_example01(args):
+    """Config C1: the reference's own Example_01 inputs (tests/golden/example_01), one normal tool
+    B5.7A0.4M, 100 measurement points, defaults of `Model.compute_synthetic_logs` (2D axisymmetric, order 3, "multigrid",
+    batch 5), mesh generation inside the timed region.  Reports log points/s (the README's 15-30 s for such a run on a
+    Ryzen 2600 is 3.3-6.7 log points/s: `vs_baseline` against the upper figure) and the parity of the log against the
+    reference's committed output."""
+    import torch
+
+    from remo3d_b200 import Model
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; this arm has no CPU fallback")
+    d = os.path.join(ROOT, "tests", "golden", "example_01")
+    gold = np.loadtxt(os.path.join(d, "Results_1.txt"), skiprows=2)
+    names = open(os.path.join(d, "Results_1.txt")).readline().split()[1:]
+    tool = "B5.7A0.4M"
+    depths = gold[75:175, 0].copy()  # 100 points, 7.5 .. 17.4 m
+    cpu = os.cpu_count() or 4
+    model = Model([tool])
+    model.set_model_parameters(os.path.join(d, "Formation.txt"), os.path.join(d, "Borehole.txt"))
+    model.initialize_workers(cpu_workers=cpu, gpu_workers=1, contexts_per_gpu=args.contexts)
+    try:
+        model.simulate_logs(depths[:5])  # warm-up (CUDA context, pool processes), untimed
+        torch.cuda.synchronize()
+        t0 = time.time()
+        model.simulate_logs(depths)
+        torch.cuda.synchronize()
+        wall = time.time() - t0
+    finally:
+        model.shutdown_workers()
+    ref = gold[75:175, names.index(tool) + 1]
+    rel = np.abs(model.logs[tool][:, 1] - ref) / ref
+    recs = [r for r in model.task_records if r and "error" not in r]
+    published = 100.0 / 15.0  # README.md:25-26, best case
+    emit({"metric": "log points/sec", "mode": "example01", "value": depths.shape[0] / wall, "unit": "log points/s", "n_gpus": 1, "steps": 1, "warmup": 1,
+          "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": depths.shape[0] / wall / published, "dtype": "f64",
+          "data": "reference example inputs (tests/golden/example_01)",
+          "config": {"workload": "C1: Examples/Example_01, tool %s, 100 depths, 2D axisymmetric, order 3, multigrid, batch 5; mesh generation inside the timed region" % tool,
+                     "tasks": len(model.task_records), "ndof_median": float(np.median([r["ndof"] for r in recs])),
+                     "iterations_median": float(np.median([max(r["iters"]) for r in recs])), "cpu_workers": cpu,
+                     "gpu_busy_fraction": model.pipeline_stats["gpu_busy_fraction"],
+                     "published": "README.md:25-26: 15-30 s for 100 points x 1 tool on a Ryzen 2600 (3.3-6.7 log points/s, end to end); vs_baseline uses 6.7",
+                     "timing": "wall clock around simulate_logs"},
+          "parity": {"max_rel_err_ra": float(rel.max()), "median_rel_err_ra": float(np.median(rel)), "n_points": int(rel.shape[0]),
+                     "against": "Examples/Example_01/Output/Results_2024_08_17__18_59_29/Results_1.txt (the reference's committed log; its own two example outputs differ by 3.1e-4)"}})
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -641,7 +688,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-companions", action="store_true", help="skip the plain-mesh and like-for-like GPU legs (N = 1 only)")
     ap.add_argument("--contexts", type=int, default=3, help="solver contexts (stream + host thread) per GPU")
-    ap.add_argument("--mode", default="step", choices=["step", "pipeline"])
+    ap.add_argument("--mode", default="step", choices=["step", "pipeline", "example01"])
     ap.add_argument("--pipeline-depths", type=int, default=1000)
     ap.add_argument("--pipeline-size", default="200k", choices=list(SIZES))
     ap.add_argument("--pipeline-improve", type=int, default=0)
@@ -651,6 +698,8 @@ def main():
         run_reference(args)
     elif args.mode == "pipeline":
         run_pipeline(args)
+    elif args.mode == "example01":
+        run_example01(args)
     else:
         run_b200(args)
 

@@ -34,8 +34,19 @@
 
 namespace {
 
-constexpr int TPB = 256;  // tets per batch = threads per CTA
-constexpr int NLD = 10;   // local dofs of the P2 tet
+// One CTA pass = one batch of tets, one tet per thread.  Order 2: 256 tets x 10 local dofs; order 3: 128 tets x 20 local dofs --
+// 2560 (tet, local dof) entries per batch either way, so every table and shared-memory array has the same size for both.
+constexpr int ENTRIES = 2560;
+constexpr int NG = 10;  // metric numbers per tet (3D: pairs (i <= j) of grad l_i . grad l_j)
+template <int NLD> struct Batch {
+  static constexpr int TPB = ENTRIES / NLD;            // tets per batch = threads per CTA
+  static constexpr int TSH = (TPB == 256) ? 8 : 7;     // log2(TPB)
+  static constexpr int NJ = 1024 / TPB;                // dofs per thread of the per-dof sums (fast8: at most 1024 dofs per batch)
+  // resident CTAs per SM the product kernel is compiled for: order 2 fits 80 registers x 768 threads; the order-3 apply holds
+  // x[20], y[20] and the metric numbers (~200 registers): 2 x 128 threads, no spills (at 3 CTAs: 1.3 KB of spills per pass)
+  static constexpr int MINB = 3;
+  static_assert(TPB == 256 || TPB == 128, "batch shapes: 256 x 10 (order 2), 128 x 20 (order 3)");
+};
 constexpr int KMAX = REMO_MAX_RHS;
 constexpr int EBE_MAX_RHS = 8;  // array bound
 constexpr int EBE_USE_RHS = 6;  // measured at 4.8 M dofs: 0.69 / 0.83 / 1.19 ms for 5 / 6 / 8 columns against 0.87 ms of the SELL kernel
@@ -73,12 +84,13 @@ __global__ void k_tet_morton(const int32_t* __restrict__ sv, const double* __res
 // (row mod 16) is least used in the piece's groups, then for every entry the free index whose scratch bank pair is least
 // used in the entry's group.  Model: 1.2 / 2.3 wavefronts per request.  Fixed visiting order -> the tables, and with
 // them the summation order of the product, are reproducible.
-template <bool FILL>
-__global__ void __launch_bounds__(TPB) k_ebe_batch(SpaceView s, const int32_t* __restrict__ tperm,
+template <bool FILL, int NLD>
+__global__ void __launch_bounds__(Batch<NLD>::TPB) k_ebe_batch(SpaceView s, const int32_t* __restrict__ tperm,
                                                    int split, int color, const uint8_t* __restrict__ constrained, int64_t* __restrict__ ucount,
                                                    int* __restrict__ umax, const int64_t* __restrict__ uoff,
                                                    int32_t* __restrict__ udof, uint16_t* __restrict__ lidx,
                                                    uint16_t* __restrict__ lpos, uint16_t* __restrict__ ucnt, uint16_t* __restrict__ jdp) {
+  constexpr int TPB = Batch<NLD>::TPB, TSH = Batch<NLD>::TSH;
   using Sort = cub::BlockRadixSort<uint32_t, TPB, NLD, uint16_t>;
   using Scan = cub::BlockScan<int, TPB>;
   constexpr int NGRP = (TPB / 16) * NLD;  // gather / scatter groups of a batch: (half-warp, slot)
@@ -101,9 +113,7 @@ __global__ void __launch_bounds__(TPB) k_ebe_batch(SpaceView s, const int32_t* _
   if (ti < s.nt) {
     const int64_t t = tperm[ti];
 #pragma unroll
-    for (int k = 0; k < 4; k++) key[k] = (uint32_t)s.sv[t * 4 + k];
-#pragma unroll
-    for (int k = 0; k < 6; k++) key[4 + k] = (uint32_t)(s.edge_base + s.elem_edges[t * 6 + k]);
+    for (int k = 0; k < NLD; k++) key[k] = (uint32_t)elem_dof(s, t, k);  // vertices, edge dofs, (order 3) face dofs
   } else {
 #pragma unroll
     for (int k = 0; k < NLD; k++) key[k] = SENT;
@@ -178,7 +188,7 @@ __global__ void __launch_bounds__(TPB) k_ebe_batch(SpaceView s, const int32_t* _
     uint32_t seen[8];
     for (int e = 0; e < n; e++) {
       const uint32_t v = sval[p0 + e];
-      const uint32_t g = ((v & (TPB - 1)) >> 4) * NLD + (v >> 8);
+      const uint32_t g = ((v & (TPB - 1)) >> 4) * NLD + (v >> TSH);
       bool dup = false;
       for (int f = 0; f < ngr; f++) dup |= seen[f] == g;
       if (!dup) seen[ngr++] = g;
@@ -257,7 +267,7 @@ __global__ void __launch_bounds__(TPB) k_ebe_batch(SpaceView s, const int32_t* _
             cost = 0;
             for (int e = 0; e < n; e++) {
               const uint32_t v = sval[p0 + e];
-              cost += G.gocc[(((v & (TPB - 1)) >> 4) * NLD + (v >> 8)) * 16 + lane];
+              cost += G.gocc[(((v & (TPB - 1)) >> 4) * NLD + (v >> TSH)) * 16 + lane];
             }
           }
         }
@@ -273,14 +283,14 @@ __global__ void __launch_bounds__(TPB) k_ebe_batch(SpaceView s, const int32_t* _
           srow[rho] = (uint16_t)row;
           for (int e = 0; e < n; e++) {
             const uint32_t v = sval[p0 + e];
-            G.gocc[(((v & (TPB - 1)) >> 4) * NLD + (v >> 8)) * 16 + r]++;
+            G.gocc[(((v & (TPB - 1)) >> 4) * NLD + (v >> TSH)) * 16 + r]++;
           }
         }
         // ---- entry order: every entry takes the free index whose scratch bank pair is least used in its group
         uint32_t avail = (1u << n) - 1u;
         for (int e = 0; e < n; e++) {
           const uint32_t v = sval[p0 + e];
-          const int g = (int)(((v & (TPB - 1)) >> 4) * NLD + (v >> 8));
+          const int g = (int)(((v & (TPB - 1)) >> 4) * NLD + (v >> TSH));
           uint32_t c2 = 0xffffu;
           if (lane < n && ((avail >> lane) & 1u)) c2 = G.socc[g * 16 + ((sjd[lane] + row) & 15)];
           uint32_t b2 = (c2 << 8) | (uint32_t)(lane & 7);
@@ -319,15 +329,16 @@ __global__ void __launch_bounds__(TPB) k_ebe_batch(SpaceView s, const int32_t* _
   }
 }
 
+template <int TPB>
 __global__ void k_ebe_gm(const double* __restrict__ gm, const int32_t* __restrict__ tperm, int64_t nt, int64_t nb,
                          double* __restrict__ gmb) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // i = b * TPB + tet
   if (i >= nb * TPB) return;
   const int64_t b = i / TPB, l = i - b * TPB;
   const bool in = i < nt;
-  const double* g = gm + (in ? (int64_t)tperm[i] : 0) * NLD;
+  const double* g = gm + (in ? (int64_t)tperm[i] : 0) * NG;
 #pragma unroll
-  for (int m = 0; m < NLD; m++) gmb[(b * NLD + m) * TPB + l] = in ? g[m] : 0.0;
+  for (int m = 0; m < NG; m++) gmb[(b * NG + m) * TPB + l] = in ? g[m] : 0.0;
 }
 
 __global__ void k_ebe_offsets_in(const int64_t* __restrict__ ucount, int64_t nb, int64_t* __restrict__ out) {
@@ -337,7 +348,7 @@ __global__ void k_ebe_offsets_in(const int64_t* __restrict__ ucount, int64_t nb,
 
 // y = K_e x for one P2 tet from its 10 metric numbers (pairs (0,0) (0,1) (0,2) (0,3) (1,1) (1,2) (1,3) (2,2) (2,3) (3,3);
 // local dofs: vertices 0..3, then the edges (0,1) (0,2) (0,3) (1,2) (1,3) (2,3) of the sorted tet)
-__device__ __forceinline__ void p2_apply(const double (&g)[NLD], const double (&x)[NLD], double (&y)[NLD]) {
+__device__ __forceinline__ void p2_apply(const double (&g)[NG], const double (&x)[10], double (&y)[10]) {
   const double S[4][4] = {{g[0], g[1], g[2], g[3]}, {g[1], g[4], g[5], g[6]}, {g[2], g[5], g[7], g[8]}, {g[3], g[6], g[8], g[9]}};
   // xe[j][a] = edge value between the local vertices j and a (0 on the diagonal)
   const double xe[4][4] = {{0.0, x[4], x[5], x[6]}, {x[4], 0.0, x[7], x[8]}, {x[5], x[7], 0.0, x[9]}, {x[6], x[8], x[9], 0.0}};
@@ -372,14 +383,19 @@ __device__ __forceinline__ void p2_apply(const double (&g)[NLD], const double (&
   for (int e = 0; e < 6; e++) y[4 + e] = (B[EA[e]] + B[EB[e]]) + 0.05 * (V[EB[e]][EA[e]] + V[EA[e]][EB[e]]);
 }
 
+// order 3: the same product straight from the exact reference tensors, symmetric pairs only (tools/gen_ebe_apply.py)
+#include "ebe_p3_apply.inc"
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(TPB, 3) k_spmm_ebe(int nb, const int64_t* __restrict__ uoff, const int32_t* __restrict__ udof,
+template <int NLD>
+__global__ void __launch_bounds__(Batch<NLD>::TPB, Batch<NLD>::MINB) k_spmm_ebe(int nb, const int64_t* __restrict__ uoff, const int32_t* __restrict__ udof,
                                                      const uint16_t* __restrict__ lidx, const uint16_t* __restrict__ lpos,
                                                      const uint16_t* __restrict__ ucnt, const uint16_t* __restrict__ jdp,
                                                      const double* __restrict__ gmb,
                                                      const double* __restrict__ P, int pstride, double* __restrict__ Q, int ks,
                                                      int nr, int xst, int umax, int fast8, int pf, double* __restrict__ partial) {
+  constexpr int TPB = Batch<NLD>::TPB, NJ = Batch<NLD>::NJ;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // xs: umax x xst staged rows of P (xst odd: random rows spread over the banks); column r is overwritten in place by
   // the batch's share of Q once pass r no longer needs it.  scr: the element results of the current pass in SORTED
@@ -400,12 +416,15 @@ __global__ void __launch_bounds__(TPB, 3) k_spmm_ebe(int nb, const int64_t* __re
     if (pf && b + (int)gridDim.x < nb) {
       // the tables of this CTA's next batch are first-touch DRAM reads: pull their lines into L2 now
       const int64_t nb1 = b + gridDim.x;
-      const void* a = nullptr;
-      if (tid < 40) a = lidx + nb1 * (TPB * NLD) + tid * 64;
-      else if (tid < 80) a = lpos + nb1 * (TPB * NLD) + (tid - 40) * 64;
-      else if (tid < 240) a = gmb + nb1 * (TPB * NLD) + (tid - 80) * 16;
-      else if (tid < 245) a = jdp + nb1 * EBE_JD + (tid - 240) * 64;
-      if (a) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+      constexpr int L_IDX = ENTRIES / 64, L_GM = NG * TPB / 16, L_JD = (EBE_JD + 63) / 64;  // 128-byte lines of each table
+      for (int i = tid; i < 2 * L_IDX + L_GM + L_JD; i += TPB) {
+        const void* a;
+        if (i < L_IDX) a = lidx + nb1 * ENTRIES + i * 64;
+        else if (i < 2 * L_IDX) a = lpos + nb1 * ENTRIES + (i - L_IDX) * 64;
+        else if (i < 2 * L_IDX + L_GM) a = gmb + nb1 * (NG * TPB) + (i - 2 * L_IDX) * 16;
+        else a = jdp + nb1 * EBE_JD + (i - 2 * L_IDX - L_GM) * 64;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+      }
       if (tid < 36) {
         const int64_t un = uoff[nb1];
         const void* a2 = tid < 24 ? (const void*)(udof + un + tid * 32) : (const void*)(ucnt + un + (tid - 24) * 64);
@@ -427,7 +446,7 @@ __global__ void __launch_bounds__(TPB, 3) k_spmm_ebe(int nb, const int64_t* __re
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     uint32_t lxo[NLD / 2], lso[NLD / 2];  // per slot: byte offset of its staged row in xs / of its sorted position in scr
-    double g[NLD];
+    double g[NG];
 #pragma unroll
     for (int k = 0; k < NLD / 2; k++) {
       const int64_t o0 = ((int64_t)b * NLD + 2 * k) * TPB + tid, o1 = o0 + TPB;
@@ -435,14 +454,15 @@ __global__ void __launch_bounds__(TPB, 3) k_spmm_ebe(int nb, const int64_t* __re
       lso[k] = ((uint32_t)__ldcs(lpos + o0) * 8u) | (((uint32_t)__ldcs(lpos + o1) * 8u) << 16);
     }
 #pragma unroll
-    for (int k = 0; k < NLD; k++) g[k] = __ldcs(gmb + ((int64_t)b * NLD + k) * TPB + tid);
-    // fast8: entry counts (+ constrained flag in bit 7) of this thread's up to four dofs, and the first 8 diagonal offsets
-    uint32_t info = 0, jdr[4] = {0, 0, 0, 0};
+    for (int k = 0; k < NG; k++) g[k] = __ldcs(gmb + ((int64_t)b * NG + k) * TPB + tid);
+    // fast8: entry counts (+ constrained flag in bit 7) of this thread's up to NJ dofs, and the first 8 diagonal offsets
+    uint64_t info = 0;
+    uint32_t jdr[4] = {0, 0, 0, 0};
     if (fast8) {
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
+      for (int j = 0; j < NJ; j++) {
         const int u = tid + j * TPB;
-        if (u < U) info |= ((uint32_t)scnt[u] | (sdof[u] < 0 ? 0x80u : 0u)) << (8 * j);
+        if (u < U) info |= (uint64_t)((uint32_t)scnt[u] | (sdof[u] < 0 ? 0x80u : 0u)) << (8 * j);
       }
 #pragma unroll
       for (int i = 0; i < 4; i++) jdr[i] = (uint32_t)sjd[2 * i] | ((uint32_t)sjd[2 * i + 1] << 16);
@@ -451,12 +471,14 @@ __global__ void __launch_bounds__(TPB, 3) k_spmm_ebe(int nb, const int64_t* __re
     __syncthreads();
     for (int r = 0; r < nr; r++) {
       {
-        double x[NLD], y[NLD];
+        double x[NLD];
         const unsigned char* xr = xs + r * 8;
 #pragma unroll
         for (int k = 0; k < NLD; k++) x[k] = *reinterpret_cast<const double*>(xr + ((lxo[k >> 1] >> ((k & 1) * 16)) & 0xffffu));
-        p2_apply(g, x, y);
         unsigned char* sb = reinterpret_cast<unsigned char*>(scr);
+        double y[NLD];
+        if constexpr (NLD == 10) p2_apply(g, x, y);
+        else p3_apply(g, x, y);
 #pragma unroll
         for (int k = 0; k < NLD; k++) *reinterpret_cast<double*>(sb + ((lso[k >> 1] >> ((k & 1) * 16)) & 0xffffu)) = y[k];
       }
@@ -468,7 +490,7 @@ __global__ void __launch_bounds__(TPB, 3) k_spmm_ebe(int nb, const int64_t* __re
         // every dof has at most 8 entries and the batch at most 1024 dofs: the diagonal offsets and this thread's entry
         // counts stay in registers for all passes (no table loads in the loop)
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < NJ; j++) {
           const int n = (int)((info >> (8 * j)) & 15u);
           if (n) {
             const int u = tid + j * TPB;
@@ -528,10 +550,12 @@ __global__ void __launch_bounds__(TPB, 3) k_spmm_ebe(int nb, const int64_t* __re
 // product kernel relies on are asserted here, once per matrix): per batch U <= umax, every dof number < ndof, every slot's
 // staged row < U, the 2560 scratch positions are a permutation of 0..2559 (no two results of a pass land on the same word),
 // every real entry sits on one of the first ucnt[row] diagonals of its row, and the entry counts add up.
-__global__ void __launch_bounds__(TPB) k_ebe_check(int64_t nt, int64_t ndof, int umax, const int64_t* __restrict__ uoff,
+template <int NLD>
+__global__ void __launch_bounds__(Batch<NLD>::TPB) k_ebe_check(int64_t nt, int64_t ndof, int umax, const int64_t* __restrict__ uoff,
                                                    const int32_t* __restrict__ udof, const uint16_t* __restrict__ lidx,
                                                    const uint16_t* __restrict__ lpos, const uint16_t* __restrict__ ucnt,
                                                    const uint16_t* __restrict__ jdp, int* __restrict__ err) {
+  constexpr int TPB = Batch<NLD>::TPB;
   __shared__ uint32_t seen[(TPB * NLD + 31) / 32];
   __shared__ int cnt_sum;
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -574,7 +598,7 @@ __global__ void __launch_bounds__(TPB) k_ebe_check(int64_t nt, int64_t ndof, int
 
 size_t ebe_smem(int umax, int nr) {
   const int xst = nr | 1;
-  return (size_t)umax * xst * 8 + (size_t)NLD * TPB * 8 + (size_t)umax * 4 + (size_t)(umax + EBE_JD) * 2;
+  return (size_t)umax * xst * 8 + (size_t)ENTRIES * 8 + (size_t)umax * 4 + (size_t)(umax + EBE_JD) * 2;
 }
 
 }  // namespace
@@ -586,7 +610,7 @@ bool ebe_eligible(const Ctx* c) {
     on = e ? atoi(e) : 1;
   }
   if (c->ebe_on >= 0 ? c->ebe_on == 0 : on == 0) return false;
-  return c->dim == 3 && c->order == 2 && c->ndof < 0x7fffffff;
+  return c->dim == 3 && (c->order == 2 || c->order == 3) && c->ndof < 0x7fffffff;
 }
 
 int ebe_max_rhs() { return EBE_USE_RHS; }
@@ -595,7 +619,11 @@ bool ebe_usable(const Ctx* c, int nr) { return c->have_ebe && nr >= 1 && nr <= E
 
 int ebe_grid(const Ctx* c, int nr) { return (int)std::min<int64_t>(c->ebe_nb, (int64_t)c->num_sms * c->ebe_occ[nr]); }
 
-void ebe_build(Ctx* c) {
+namespace {
+
+template <int NLD>
+void ebe_build_t(Ctx* c) {
+  constexpr int TPB = Batch<NLD>::TPB;
   cudaStream_t st = c->stream;
   const int64_t nt = c->nt, nb = (nt + TPB - 1) / TPB;
   size_t bytes = 0;
@@ -604,7 +632,7 @@ void ebe_build(Ctx* c) {
   uint64_t* codes = scratch<uint64_t>(c, 1, nt);
   int32_t* idx = scratch<int32_t>(c, 2, nt);
   int32_t* tperm = scratch<int32_t>(c, 3, nt);
-  LAUNCH(c, k_tet_morton, grid_for(nt, TPB), TPB, 0, c->sv.p, c->xyz.p, mesh_bbox(c), nt, code, idx);
+  LAUNCH(c, k_tet_morton, grid_for(nt, 256), 256, 0, c->sv.p, c->xyz.p, mesh_bbox(c), nt, code, idx);
   CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, code, codes, idx, tperm, nt, 0, 63, st));
   c->tmp.ensure(bytes, st);
   CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, code, codes, idx, tperm, nt, 0, 63, st));
@@ -617,8 +645,8 @@ void ebe_build(Ctx* c) {
   CK(cudaMemsetAsync(umax_d, 0, sizeof(int), st));
   SpaceView sview = make_view(c);
   static const int color = [] { const char* e = getenv("REMO_EBE_COLOR"); return e ? atoi(e) : 0; }();  // off until the greedy build is cheap (53 ms at 4.8 M dofs for 0.05 ms per product)
-  LAUNCH(c, k_ebe_batch<false>, (unsigned)nb, TPB, 0, sview, tperm, split, color, c->constrained.p, ucount, umax_d, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
-  LAUNCH(c, k_ebe_offsets_in, grid_for(nb + 1, TPB), TPB, 0, ucount, nb, uin);
+  LAUNCH(c, (k_ebe_batch<false, NLD>), (unsigned)nb, TPB, 0, sview, tperm, split, color, c->constrained.p, ucount, umax_d, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  LAUNCH(c, k_ebe_offsets_in, grid_for(nb + 1, 256), 256, 0, ucount, nb, uin);
   c->ebe_uoff.ensure(nb + 1, st);
   CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, uin, c->ebe_uoff.p, nb + 1, st));
   c->tmp.ensure(bytes, st);
@@ -634,32 +662,32 @@ void ebe_build(Ctx* c) {
   c->ebe_udof.ensure(total, st);
   c->ebe_ucnt.ensure(total, st);
   c->ebe_jd.ensure((size_t)nb * EBE_JD, st);
-  c->ebe_lidx.ensure((size_t)nb * TPB * NLD, st);
-  c->ebe_lpos.ensure((size_t)nb * TPB * NLD, st);
-  c->ebe_gm.ensure((size_t)nb * TPB * NLD, st);
-  LAUNCH(c, k_ebe_batch<true>, (unsigned)nb, TPB, 0, sview, tperm, split, color, c->constrained.p, nullptr, nullptr, c->ebe_uoff.p, c->ebe_udof.p,
+  c->ebe_lidx.ensure((size_t)nb * ENTRIES, st);
+  c->ebe_lpos.ensure((size_t)nb * ENTRIES, st);
+  c->ebe_gm.ensure((size_t)nb * TPB * NG, st);
+  LAUNCH(c, (k_ebe_batch<true, NLD>), (unsigned)nb, TPB, 0, sview, tperm, split, color, c->constrained.p, nullptr, nullptr, c->ebe_uoff.p, c->ebe_udof.p,
          c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_ucnt.p, c->ebe_jd.p);
-  LAUNCH(c, k_ebe_gm, grid_for(nb * TPB, TPB), TPB, 0, c->gm.p, tperm, nt, nb, c->ebe_gm.p);
+  LAUNCH(c, k_ebe_gm<TPB>, grid_for(nb * TPB, 256), 256, 0, c->gm.p, tperm, nt, nb, c->ebe_gm.p);
   c->ebe_nb = nb;
-  c->ebe_fast8 = (split > 0 && split <= 8 && umax <= 4 * TPB) ? 1 : 0;
+  c->ebe_nld = NLD;
+  c->ebe_fast8 = (split > 0 && split <= 8 && umax <= Batch<NLD>::NJ * TPB) ? 1 : 0;
   c->ebe_umax = umax;
   // resident CTAs per SM for every right-hand-side count (the shared-memory row stride of xs depends on it)
-  int dev_max = 0;
-  CK(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-  const size_t top = std::min<size_t>(ebe_smem(umax, EBE_MAX_RHS), (size_t)dev_max);
-  CK(cudaFuncSetAttribute(k_spmm_ebe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)top));
+  // raised once per (kernel, device) to the opt-in maximum, never to a per-mesh value: other contexts of this GPU launch the
+  // same kernel for other meshes (ctx.cuh allow_max_smem)
+  const int dev_max = allow_max_smem(k_spmm_ebe<NLD>, c->device);
   for (int nr = 1; nr <= EBE_MAX_RHS; nr++) {
     const size_t sm = ebe_smem(umax, nr);
     int occ = 0;
     // the kernel keeps byte offsets into xs as 16-bit numbers
-    if (sm <= (size_t)dev_max && (size_t)umax * (nr | 1) * 8 < 65536) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_ebe, TPB, sm));
+    if (sm <= (size_t)dev_max && (size_t)umax * (nr | 1) * 8 < 65536) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_ebe<NLD>, TPB, sm));
     c->ebe_occ[nr] = occ;  // 0: a batch does not fit (degenerate mesh) -> the SELL / CSR kernels take over
   }
   if (c->ebe_check) {
     int* err_d = scratch<int>(c, 6, 1);
     int err = 0;
     CK(cudaMemsetAsync(err_d, 0, sizeof(int), st));
-    LAUNCH(c, k_ebe_check, (unsigned)nb, TPB, 0, nt, c->ndof, umax, c->ebe_uoff.p, c->ebe_udof.p, c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_ucnt.p, c->ebe_jd.p, err_d);
+    LAUNCH(c, k_ebe_check<NLD>, (unsigned)nb, TPB, 0, nt, c->ndof, umax, c->ebe_uoff.p, c->ebe_udof.p, c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_ucnt.p, c->ebe_jd.p, err_d);
     CK(cudaMemcpyAsync(&err, err_d, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (err) FAIL(REMO_ERR_STATE, "ebe_check: %d violations in the batch tables", err);
@@ -667,15 +695,28 @@ void ebe_build(Ctx* c) {
   c->have_ebe = true;
 }
 
-void launch_spmm_ebe(Ctx* c, const double* P, int pstride, double* Q, int ks, int nr) {
+template <int NLD>
+void launch_t(Ctx* c, const double* P, int pstride, double* Q, int ks, int nr) {
   cudaStream_t st = c->stream;
-  CK(cudaMemsetAsync(Q, 0, (size_t)c->ndof * ks * sizeof(double), st));
   const int xst = nr | 1;
   const int grid = ebe_grid(c, nr);
   static const int pf = [] { const char* e = getenv("REMO_EBE_PREFETCH"); return e ? atoi(e) : 1; }();
   const size_t sm = ebe_smem(c->ebe_umax, nr);
-  k_spmm_ebe<<<grid, TPB, sm, st>>>((int)c->ebe_nb, c->ebe_uoff.p, c->ebe_udof.p, c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_ucnt.p, c->ebe_jd.p, c->ebe_gm.p,
-                                    P, pstride, Q, ks, nr, xst, c->ebe_umax, c->ebe_fast8, pf, c->partial.p);
+  k_spmm_ebe<NLD><<<grid, Batch<NLD>::TPB, sm, st>>>((int)c->ebe_nb, c->ebe_uoff.p, c->ebe_udof.p, c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_ucnt.p, c->ebe_jd.p,
+                                                       c->ebe_gm.p, P, pstride, Q, ks, nr, xst, c->ebe_umax, c->ebe_fast8, pf, c->partial.p);
+}
+
+}  // namespace
+
+void ebe_build(Ctx* c) {
+  if (c->order == 3) ebe_build_t<20>(c);
+  else ebe_build_t<10>(c);
+}
+
+void launch_spmm_ebe(Ctx* c, const double* P, int pstride, double* Q, int ks, int nr) {
+  CK(cudaMemsetAsync(Q, 0, (size_t)c->ndof * ks * sizeof(double), c->stream));
+  if (c->ebe_nld == 20) launch_t<20>(c, P, pstride, Q, ks, nr);
+  else launch_t<10>(c, P, pstride, Q, ks, nr);
   c->launches += 2;
   CK(cudaGetLastError());
 }

@@ -444,33 +444,39 @@ def _check_spmm(ctx, ks, seed=5):
         assert np.max(abs(pq - dots) / (abs(P * ref).sum(0))) <= 1e-13, k
 
 
-@pytest.mark.parametrize("dim,order,ebe", [(3, 1, 1), (3, 2, 1), (3, 2, 0), (3, 3, 1), (2, 2, 1), (2, 3, 1)])
+@pytest.mark.parametrize("dim,order,ebe", [(3, 1, 1), (3, 2, 1), (3, 2, 0), (3, 3, 1), (3, 3, 0), (2, 2, 1), (2, 3, 1)])
 def test_spmm_kernels_against_scipy(ctx, dim, order, ebe):
     """Every SpMM kernel the PCG can pick (CSR one-column, SELL generic for strides 2/4/16/32, SELL streaming for 5..8
-    right-hand sides, and the element-wise product of ebe.cu, which order-2 tets take for up to 8 right-hand sides unless
-    switched off) against the exact product with the oracle-checked CSR matrix: Q = A P on free rows, 0 on constrained
+    right-hand sides, and the element-wise product of ebe.cu, which order-2 AND order-3 tets take for up to 6 right-hand sides
+    unless switched off) against the exact product with the oracle-checked CSR matrix: Q = A P on free rows, 0 on constrained
     rows, and the fused per-column dots p.q."""
     mesh, sigma = (helpers.ball_case() if dim == 3 else helpers.disc_case())[:2]
     ctx.set_option("spmm_ebe", ebe)
     try:
         _setup(ctx, mesh, order)
         ctx.assemble(sigma)
+        ctx.set_option("ebe_check", 1)
         _check_spmm(ctx, (1, 2, 3, 4, 5, 6, 7, 8, 9, 16, 17, 32))
+        if dim == 3 and order in (2, 3):
+            ctx.spmm_apply(np.ones((ctx.ndof, 5)))
+            assert ctx.spmm_kind() == (2 if ebe else 1), ctx.spmm_kind()  # 2 = element-wise product, 1 = SELL copy
     finally:
+        ctx.set_option("ebe_check", 0)
         ctx.set_option("spmm_ebe", 1)
 
 
 def test_elementwise_spmm_on_degenerate_batches(ctx):
     """ebe.cu on the star mesh: one vertex belongs to every tet, so inside a batch of 256 tets one dof has 256 entries
     (the longest jagged diagonal) next to edges with 2-3; and on a mesh smaller than one batch."""
-    mesh, sigma = helpers.star_case()
-    _setup(ctx, mesh, 2)
-    ctx.assemble(sigma)
-    _check_spmm(ctx, (1, 5, 6), seed=7)
-    mesh, sigma = helpers.box_case(2)
-    _setup(ctx, mesh, 2)
-    ctx.assemble(sigma)
-    _check_spmm(ctx, (2, 5), seed=8)
+    for order in (2, 3):
+        mesh, sigma = helpers.star_case(nsphere=260 if order == 2 else 120)  # order 3: the row of the centre stays below the assembly limit
+        _setup(ctx, mesh, order)
+        ctx.assemble(sigma)
+        _check_spmm(ctx, (1, 5, 6), seed=7)
+        mesh, sigma = helpers.box_case(2)
+        _setup(ctx, mesh, order)
+        ctx.assemble(sigma)
+        _check_spmm(ctx, (2, 5), seed=8)
 
 
 @pytest.mark.parametrize("order", [2, 3])

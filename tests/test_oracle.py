@@ -168,3 +168,21 @@ def test_jacobi_pcg_matches_direct():
     a = fo.solve_task(mesh.points, mesh.elems, mesh.mat, sigma, mesh.bfacets, mesh.dirichlet_flags("dirichlet_boundary"), 1, flat, solver="direct")
     b = fo.solve_task(mesh.points, mesh.elems, mesh.mat, sigma, mesh.bfacets, mesh.dirichlet_flags("dirichlet_boundary"), 1, flat, solver="pcg")
     np.testing.assert_allclose(a["ra"], b["ra"], rtol=1e-9)
+
+
+def test_p3_tet_pair_list_matches_tensors():
+    """csrc/ebe_p3_apply.inc (order-3 element-wise product) is generated from the symmetric pair list of the exact reference
+    tensors: its NumPy emulation equals K x, and the committed file is what the generator emits."""
+    import importlib.util
+    import os
+    import tempfile
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_ebe_apply", os.path.join(root, "tools", "gen_ebe_apply.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    assert gen.check() < 1e-14
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "p3.inc")
+        gen.emit(path)
+        assert open(path).read() == open(os.path.join(root, "remo3d_b200", "csrc", "ebe_p3_apply.inc")).read()
