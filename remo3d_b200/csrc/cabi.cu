@@ -403,6 +403,7 @@ int remo_set_option(void* vctx, const char* name, double value) {
     const std::string n(name);
     if (n == "amg_alpha") c->amg_alpha = value;
     else if (n == "amg_sweeps") c->amg_sweeps = std::max(1, (int)value);
+    else if (n == "ebe_p3_ctas") { c->ebe_p3_ctas = (int)value; c->have_ebe = false; c->pkind = -1; }
     else if (n == "ebe_check") { c->ebe_check = value != 0.0 ? 1 : 0; c->have_ebe = false; c->pkind = -1; }
     else if (n == "spmm_ebe") { c->ebe_on = value != 0.0 ? 1 : 0; c->have_ebe = false; c->pkind = -1; }
     else if (n == "amg_omega_scale") { c->amg_omega_scale = value; c->pkind = -1; }

@@ -130,6 +130,7 @@ struct Ctx {
   int ebe_fast8 = 0;  // every dof piece has <= 8 entries and every batch <= 1024 of them: register tables in the kernel
   int ebe_occ[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // resident CTAs per SM by right-hand-side count
   bool have_ebe = false;
+  int ebe_p3_ctas = 3;  // order-3 product kernel build: 3 (168 registers) or 4 (128 registers) resident CTAs per SM
   int ebe_nld = 10;  // local dofs per tet of the tables in use: 10 (order 2, batches of 256 tets) or 20 (order 3, batches of 128)
   int ebe_check = 0;  // remo_set_option("ebe_check", 1): validate the batch tables after every build (ebe.cu k_ebe_check)
   int ebe_on = -1;  // remo_set_option("spmm_ebe"): 0 / 1, -1 = the REMO_SPMM_EBE environment default (on)

@@ -1,5 +1,8 @@
-// Element-wise multi-right-hand-side product Q = A P (+ fused p.q) for order-2 tetrahedra: the PCG "SpMM" without the
-// assembled matrix.
+// Element-wise multi-right-hand-side product Q = A P (+ fused p.q) for order-2 and order-3 tetrahedra: the PCG "SpMM" without
+// the assembled matrix.  (Written for order 2 first -- the text below; order 3 is the same kernel on batches of 128 tets x 20
+// local dofs with the element product generated from the exact reference tensors, see Batch<NLD> and ebe_p3_apply.inc:
+// 0.685 ms for 5 right-hand sides at 4.75 M dofs / 227.6 M nnz = 70 % of the HBM roofline by the bytes of the SpMM it
+// replaces, against 1.353 ms of the SELL kernel.)
 //
 // Why.  The CSR / SELL SpMM gathers one 64-byte row of P per matrix entry (136.9 M gathers at 4.8 M dofs) and is bound
 // by the latency x concurrency of those gathers at ~36 % of the HBM roofline (profiles/r01_notes.md).  The same product
@@ -388,8 +391,8 @@ __device__ __forceinline__ void p2_apply(const double (&g)[NG], const double (&x
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int NLD>
-__global__ void __launch_bounds__(Batch<NLD>::TPB, Batch<NLD>::MINB) k_spmm_ebe(int nb, const int64_t* __restrict__ uoff, const int32_t* __restrict__ udof,
+template <int NLD, int MINB = Batch<NLD>::MINB>
+__global__ void __launch_bounds__(Batch<NLD>::TPB, MINB) k_spmm_ebe(int nb, const int64_t* __restrict__ uoff, const int32_t* __restrict__ udof,
                                                      const uint16_t* __restrict__ lidx, const uint16_t* __restrict__ lpos,
                                                      const uint16_t* __restrict__ ucnt, const uint16_t* __restrict__ jdp,
                                                      const double* __restrict__ gmb,
@@ -675,12 +678,16 @@ void ebe_build_t(Ctx* c) {
   // resident CTAs per SM for every right-hand-side count (the shared-memory row stride of xs depends on it)
   // raised once per (kernel, device) to the opt-in maximum, never to a per-mesh value: other contexts of this GPU launch the
   // same kernel for other meshes (ctx.cuh allow_max_smem)
-  const int dev_max = allow_max_smem(k_spmm_ebe<NLD>, c->device);
+  const bool four = NLD == 20 && c->ebe_p3_ctas >= 4;  // order 3: the 128-register build (4 resident CTAs, 240 B of spills)
+  const int dev_max = four ? allow_max_smem(k_spmm_ebe<NLD, 4>, c->device) : allow_max_smem(k_spmm_ebe<NLD>, c->device);
   for (int nr = 1; nr <= EBE_MAX_RHS; nr++) {
     const size_t sm = ebe_smem(umax, nr);
     int occ = 0;
     // the kernel keeps byte offsets into xs as 16-bit numbers
-    if (sm <= (size_t)dev_max && (size_t)umax * (nr | 1) * 8 < 65536) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_ebe<NLD>, TPB, sm));
+    if (sm <= (size_t)dev_max && (size_t)umax * (nr | 1) * 8 < 65536) {
+      if (four) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_ebe<NLD, 4>, TPB, sm));
+      else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_ebe<NLD>, TPB, sm));
+    }
     c->ebe_occ[nr] = occ;  // 0: a batch does not fit (degenerate mesh) -> the SELL / CSR kernels take over
   }
   if (c->ebe_check) {
@@ -702,8 +709,12 @@ void launch_t(Ctx* c, const double* P, int pstride, double* Q, int ks, int nr) {
   const int grid = ebe_grid(c, nr);
   static const int pf = [] { const char* e = getenv("REMO_EBE_PREFETCH"); return e ? atoi(e) : 1; }();
   const size_t sm = ebe_smem(c->ebe_umax, nr);
-  k_spmm_ebe<NLD><<<grid, Batch<NLD>::TPB, sm, st>>>((int)c->ebe_nb, c->ebe_uoff.p, c->ebe_udof.p, c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_ucnt.p, c->ebe_jd.p,
-                                                       c->ebe_gm.p, P, pstride, Q, ks, nr, xst, c->ebe_umax, c->ebe_fast8, pf, c->partial.p);
+  if (NLD == 20 && c->ebe_p3_ctas >= 4)
+    k_spmm_ebe<NLD, 4><<<grid, Batch<NLD>::TPB, sm, st>>>((int)c->ebe_nb, c->ebe_uoff.p, c->ebe_udof.p, c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_ucnt.p,
+                                                            c->ebe_jd.p, c->ebe_gm.p, P, pstride, Q, ks, nr, xst, c->ebe_umax, c->ebe_fast8, pf, c->partial.p);
+  else
+    k_spmm_ebe<NLD><<<grid, Batch<NLD>::TPB, sm, st>>>((int)c->ebe_nb, c->ebe_uoff.p, c->ebe_udof.p, c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_ucnt.p, c->ebe_jd.p,
+                                                         c->ebe_gm.p, P, pstride, Q, ks, nr, xst, c->ebe_umax, c->ebe_fast8, pf, c->partial.p);
 }
 
 }  // namespace

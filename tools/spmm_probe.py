@@ -14,6 +14,9 @@ a = ap.parse_args()
 task, flat = bench.make_task()
 m = bench.make_mesh(a.size, task, print)
 ctx = _cabi.Context(0)
+for kv in os.environ.get("REMO_BENCH_OPTS", "").split(","):
+    if "=" in kv:
+        ctx.set_option(kv.split("=")[0].strip(), float(kv.split("=")[1]))
 ctx.mesh_set(3, m["points"], m["elems"], m["mat"], m["bfacets"], m["bdir"], m["axis"])
 ndof, _ = ctx.space_build(a.order); nnz = ctx.nnz
 ctx.assemble(bench.SIGMA)
