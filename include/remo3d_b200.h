@@ -70,7 +70,7 @@ int remo_mesh_set(void* ctx, int dim, int64_t nv, const double* xyz, int64_t nt,
  * (replaces `fes = ngs.H1(mesh, order=3, dirichlet=..)`, ngsolve_functions.py:27, and the
  * sparsity-graph part of `a.Assemble()`, :47).  order in {1,2,3}.
  * The CSR pattern itself is built on demand (remo_matrix_nnz / remo_matrix_get / a solve that
- * reads the assembled matrix): the element-wise PCG path of order-2 tets never needs it.  *nnz is
+ * reads the assembled matrix): the element-wise PCG path of order-2 / order-3 tets never needs it.  *nnz is
  * 0 unless the pattern exists when the call returns (remo_set_option("lazy_matrix", 0): always). */
 int remo_space_build(void* ctx, int order, int64_t* ndof, int64_t* nnz, int64_t* nedges, int64_t* nfaces);
 
@@ -139,11 +139,16 @@ int remo_kernel_time(void* ctx, int which, int nrhs, int reps, float* ms);
  * right-hand sides and the solution of the context.                                                            */
 int remo_spmm_apply(void* ctx, int nrhs, const double* p, double* q, double* pq);
 /* Which SpMM the PCG uses for the right-hand sides currently set: 0 = CSR kernels, 1 = SELL-8 copy (sell.cu),
- * 2 = element-wise product from the metric numbers, no assembled matrix read (ebe.cu: order-2 tets, <= 6 columns). */
+ * 2 = element-wise product from the metric numbers, no assembled matrix read (ebe.cu: order-2 / order-3 tets, <= 6 columns). */
 int remo_spmm_kind(void* ctx);
 /* Solver tunables (defaults in parentheses): "amg_sweeps" (1) pre = post damped-Jacobi sweeps per AMG level,
  * "amg_alpha" (1.5) scaling of the coarse-grid correction, "spmm_ebe" (1) 0 switches the element-wise product off (the SELL kernels take over), "amg_omega_scale" (1.0) weight of the l1-Jacobi sweeps,
- * must be <= 1 (changing it invalidates the preconditioner: call remo_precond_setup again).                        */
+ * must be <= 1 (changing it invalidates the preconditioner: call remo_precond_setup again).
+ * Round 2: "amg_fp32" (1) the V-cycle runs in fp32 inside the fp64 PCG; "amg_lanes8" (1) 8 lanes per row in the sweeps for 5..8
+ * columns; "amg_fused_tail" (0) / "amg_tail_rows" (20000) small levels in one cluster kernel; "amg_agg" (1) strength-based
+ * pairwise aggregation (0: Morton-rank aggregates), "amg_passes" (3), "amg_rounds" (4); "ebe_check" (0) validate the
+ * element-wise batch tables after every build (fails with REMO_ERR_STATE on a violation); "ebe_p3_ctas" (3) build of the
+ * order-3 product kernel: 3 or 4 resident CTAs per SM; "lazy_matrix" (1) CSR pattern / values only on demand.          */
 int remo_set_option(void* ctx, const char* name, double value);
 /* Per-launch timing of the SpMM inside remo_solve: while on, CUDA events bracket every SpMM launch of the
  * PCG loop on the context's stream; remo_profile_get returns the summed milliseconds and the launch count

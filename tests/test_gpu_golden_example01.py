@@ -59,3 +59,28 @@ def test_example01_logs_match_reference_output(golden_dir):
         worst = max(worst, rel.max())
     assert all(r is not None and "error" not in r for r in model.task_records), model.task_records
     assert worst < TOL, worst
+
+
+def test_example01_3d_path_at_the_reference_order(golden_dir):
+    """The same log through the 3D path at ORDER 3 (what the reference hard-wires, `ngsolve_functions.py:27`; the `Model`
+    default): the order-3 element-wise product + the mixed-precision V-cycle end to end.  Coarser near field than the order-2
+    test (17 k vertices, 440 k dofs per mesh): the CPU oracle on the same mesh is at -5.4e-3 (interface representation, not the
+    polynomial order, carries the difference), bound 1e-2."""
+    from remo3d_b200 import Model
+
+    d = os.path.join(golden_dir, "example_01")
+    gold = np.loadtxt(os.path.join(d, "Results_1.txt"), skiprows=2)
+    names = open(os.path.join(d, "Results_1.txt")).readline().split()[1:]
+    tools = ["A2.0M0.5N", "N0.5M2.0A"]
+    depths = np.array([5.5, 15.5])
+    model = Model.compute_synthetic_logs(tools, depths, os.path.join(d, "Formation.txt"), os.path.join(d, "Borehole.txt"),
+                                         dip=0.01, cpu_workers=4, gpu_workers=1,
+                                         mesh_options={"h_electrode": 0.03, "h_axis": 0.08, "grading": 0.35})
+    assert all(r is not None and "error" not in r for r in model.task_records), model.task_records
+    worst = 0.0
+    for t in tools:
+        ref = np.array([gold[np.argmin(np.abs(gold[:, 0] - z)), names.index(t) + 1] for z in depths])
+        rel = np.abs(model.logs[t][:, 1] - ref) / ref
+        print(t, "reference", ref, "this repo", np.round(model.logs[t][:, 1], 4), "rel", np.round(rel, 4))
+        worst = max(worst, rel.max())
+    assert worst < TOL, worst
