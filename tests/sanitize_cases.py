@@ -1,4 +1,4 @@
-"""Small cases for compute-sanitizer (tools/sanitize.sh): every SpMM kind (element-wise product, SELL streaming / generic, CSR
+"""Small cases for compute-sanitizer (tools/sanitize.sh; kept under tests/ because the oracle is the checker): every SpMM kind (element-wise product, SELL streaming / generic, CSR
 one-column), both preconditioners, orders 1-3, 3D and 2D, 1 / 5 / 8 right-hand sides -- each checked against the oracle."""
 import os
 import sys
@@ -7,7 +7,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 import helpers  # noqa: E402
 from oracle import fem_oracle as fo  # noqa: E402
