@@ -139,7 +139,7 @@ int remo_kernel_time(void* ctx, int which, int nrhs, int reps, float* ms);
  * right-hand sides and the solution of the context.                                                            */
 int remo_spmm_apply(void* ctx, int nrhs, const double* p, double* q, double* pq);
 /* Which SpMM the PCG uses for the right-hand sides currently set: 0 = CSR kernels, 1 = SELL-8 copy (sell.cu),
- * 2 = element-wise product from the metric numbers, no assembled matrix read (ebe.cu: order-2 / order-3 tets, <= 6 columns). */
+ * 2 = element-wise product from the metric numbers, no assembled matrix read (ebe.cu: order-2 / order-3 tets, order-3 triangles, <= 6 columns). */
 int remo_spmm_kind(void* ctx);
 /* Solver tunables (defaults in parentheses): "amg_sweeps" (1) pre = post damped-Jacobi sweeps per AMG level,
  * "amg_alpha" (1.5) scaling of the coarse-grid correction, "spmm_ebe" (1) 0 switches the element-wise product off (the SELL kernels take over), "amg_omega_scale" (1.0) weight of the l1-Jacobi sweeps,

@@ -131,6 +131,7 @@ struct Ctx {
   int ebe_occ[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // resident CTAs per SM by right-hand-side count
   bool have_ebe = false;
   int ebe_p3_ctas = 3;  // order-3 product kernel build: 3 (168 registers) or 4 (128 registers) resident CTAs per SM
+  int ebe_ng = 10;   // metric numbers per element of the tables in use: 10 (tets) or 18 (axisymmetric triangles)
   int ebe_nld = 10;  // local dofs per tet of the tables in use: 10 (order 2, batches of 256 tets) or 20 (order 3, batches of 128)
   int ebe_check = 0;  // remo_set_option("ebe_check", 1): validate the batch tables after every build (ebe.cu k_ebe_check)
   int ebe_on = -1;  // remo_set_option("spmm_ebe"): 0 / 1, -1 = the REMO_SPMM_EBE environment default (on)
@@ -281,7 +282,7 @@ void alloc_solver_state(Ctx* c, int nrhs);
 int spmm_variant();
 void spmm_prepare(Ctx* c);
 int spmm_kind(Ctx* c);
-int solver_stride(const Ctx* c, int nrhs);  // row stride of the PCG vector blocks for nrhs right-hand sides
+int solver_stride(Ctx* c, int nrhs);  // row stride of the PCG vector blocks for nrhs right-hand sides
 int spmm_blocks(Ctx* c, int ks);   // CTAs (= partial-dot slots) of the SpMM launch for stride ks
 // sell.cu
 const double* mesh_bbox(Ctx* c);
@@ -291,6 +292,7 @@ int sell_grid(const Ctx* c);
 void launch_spmm_sell(Ctx* c, const double* P, double* Q, int ks, int pstride);
 // ebe.cu
 bool ebe_eligible(const Ctx* c);
+bool ebe_serves(Ctx* c, int nr);
 bool ebe_usable(const Ctx* c, int nr);
 int ebe_max_rhs();
 void ebe_build(Ctx* c);

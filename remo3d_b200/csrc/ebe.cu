@@ -2,7 +2,8 @@
 // the assembled matrix.  (Written for order 2 first -- the text below; order 3 is the same kernel on batches of 128 tets x 20
 // local dofs with the element product generated from the exact reference tensors, see Batch<NLD> and ebe_p3_apply.inc:
 // 0.685 ms for 5 right-hand sides at 4.75 M dofs / 227.6 M nnz = 70 % of the HBM roofline by the bytes of the SpMM it
-// replaces, against 1.353 ms of the SELL kernel.)
+// replaces, against 1.353 ms of the SELL kernel.  Order-3 axisymmetric triangles -- the reference's default 2D configuration --
+// use the 256 x 10 shape with 18 metric numbers per element and p3tri_apply.)
 //
 // Why.  The CSR / SELL SpMM gathers one 64-byte row of P per matrix entry (136.9 M gathers at 4.8 M dofs) and is bound
 // by the latency x concurrency of those gathers at ~36 % of the HBM roofline (profiles/r01_notes.md).  The same product
@@ -40,7 +41,8 @@ namespace {
 // One CTA pass = one batch of tets, one tet per thread.  Order 2: 256 tets x 10 local dofs; order 3: 128 tets x 20 local dofs --
 // 2560 (tet, local dof) entries per batch either way, so every table and shared-memory array has the same size for both.
 constexpr int ENTRIES = 2560;
-constexpr int NG = 10;  // metric numbers per tet (3D: pairs (i <= j) of grad l_i . grad l_j)
+// metric numbers per element: NG = 10 on tets (pairs (i <= j) of grad l_i . grad l_j), 18 on axisymmetric triangles (6 pairs x
+// the 3 weights r_k); shapes in use: <NLD, NG> = <10, 10> order-2 tets, <20, 10> order-3 tets, <10, 18> order-3 triangles
 template <int NLD> struct Batch {
   static constexpr int TPB = ENTRIES / NLD;            // tets per batch = threads per CTA
   static constexpr int TSH = (TPB == 256) ? 8 : 7;     // log2(TPB)
@@ -56,15 +58,18 @@ constexpr int EBE_USE_RHS = 6;  // measured at 4.8 M dofs: 0.69 / 0.83 / 1.19 ms
 constexpr uint32_t SENT = 0xffffffffu;
 constexpr int EBE_JD = 264;  // jagged-diagonal offsets kept per batch (a dof has at most 256 entries in a batch)
 
+template <int DIM>
 __global__ void k_tet_morton(const int32_t* __restrict__ sv, const double* __restrict__ xyz, const double* __restrict__ lohi,
                              int64_t nt, uint64_t* __restrict__ code, int32_t* __restrict__ idx) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= nt) return;
-  const int4 v = reinterpret_cast<const int4*>(sv)[t];
   uint64_t c = 0;
 #pragma unroll
-  for (int d = 0; d < 3; d++) {
-    const double x = 0.25 * (xyz[3 * (int64_t)v.x + d] + xyz[3 * (int64_t)v.y + d] + xyz[3 * (int64_t)v.z + d] + xyz[3 * (int64_t)v.w + d]);
+  for (int d = 0; d < DIM; d++) {
+    double x = 0.0;
+#pragma unroll
+    for (int i = 0; i <= DIM; i++) x += xyz[DIM * (int64_t)sv[t * (DIM + 1) + i] + d];
+    x *= 1.0 / (DIM + 1);
     const double ext = lohi[3 + d] - lohi[d];
     const double u = ext > 0 ? (x - lohi[d]) / ext : 0.0;
     const uint64_t q = (uint64_t)fmin(fmax(u * 2097151.0, 0.0), 2097151.0);
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(Batch<NLD>::TPB) k_ebe_batch(SpaceView s, cons
   }
 }
 
-template <int TPB>
+template <int TPB, int NG>
 __global__ void k_ebe_gm(const double* __restrict__ gm, const int32_t* __restrict__ tperm, int64_t nt, int64_t nb,
                          double* __restrict__ gmb) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // i = b * TPB + tet
@@ -351,7 +356,7 @@ __global__ void k_ebe_offsets_in(const int64_t* __restrict__ ucount, int64_t nb,
 
 // y = K_e x for one P2 tet from its 10 metric numbers (pairs (0,0) (0,1) (0,2) (0,3) (1,1) (1,2) (1,3) (2,2) (2,3) (3,3);
 // local dofs: vertices 0..3, then the edges (0,1) (0,2) (0,3) (1,2) (1,3) (2,3) of the sorted tet)
-__device__ __forceinline__ void p2_apply(const double (&g)[NG], const double (&x)[10], double (&y)[10]) {
+__device__ __forceinline__ void p2_apply(const double (&g)[10], const double (&x)[10], double (&y)[10]) {
   const double S[4][4] = {{g[0], g[1], g[2], g[3]}, {g[1], g[4], g[5], g[6]}, {g[2], g[5], g[7], g[8]}, {g[3], g[6], g[8], g[9]}};
   // xe[j][a] = edge value between the local vertices j and a (0 on the diagonal)
   const double xe[4][4] = {{0.0, x[4], x[5], x[6]}, {x[4], 0.0, x[7], x[8]}, {x[5], x[7], 0.0, x[9]}, {x[6], x[8], x[9], 0.0}};
@@ -391,7 +396,7 @@ __device__ __forceinline__ void p2_apply(const double (&g)[NG], const double (&x
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int NLD, int MINB = Batch<NLD>::MINB>
+template <int NLD, int NG, int MINB = (NG == 18 ? 2 : Batch<NLD>::MINB)>  // triangles: 18 metric numbers live, 2 CTAs
 __global__ void __launch_bounds__(Batch<NLD>::TPB, MINB) k_spmm_ebe(int nb, const int64_t* __restrict__ uoff, const int32_t* __restrict__ udof,
                                                      const uint16_t* __restrict__ lidx, const uint16_t* __restrict__ lpos,
                                                      const uint16_t* __restrict__ ucnt, const uint16_t* __restrict__ jdp,
@@ -480,8 +485,9 @@ __global__ void __launch_bounds__(Batch<NLD>::TPB, MINB) k_spmm_ebe(int nb, cons
         for (int k = 0; k < NLD; k++) x[k] = *reinterpret_cast<const double*>(xr + ((lxo[k >> 1] >> ((k & 1) * 16)) & 0xffffu));
         unsigned char* sb = reinterpret_cast<unsigned char*>(scr);
         double y[NLD];
-        if constexpr (NLD == 10) p2_apply(g, x, y);
-        else p3_apply(g, x, y);
+        if constexpr (NLD == 10 && NG == 10) p2_apply(g, x, y);
+        else if constexpr (NLD == 20) p3_apply(g, x, y);
+        else p3tri_apply(g, x, y);
 #pragma unroll
         for (int k = 0; k < NLD; k++) *reinterpret_cast<double*>(sb + ((lso[k >> 1] >> ((k & 1) * 16)) & 0xffffu)) = y[k];
       }
@@ -613,10 +619,21 @@ bool ebe_eligible(const Ctx* c) {
     on = e ? atoi(e) : 1;
   }
   if (c->ebe_on >= 0 ? c->ebe_on == 0 : on == 0) return false;
-  return c->dim == 3 && (c->order == 2 || c->order == 3) && c->ndof < 0x7fffffff;
+  if (c->ndof >= 0x7fffffff) return false;
+  return (c->dim == 3 && (c->order == 2 || c->order == 3)) || (c->dim == 2 && c->order == 3);
 }
 
 int ebe_max_rhs() { return EBE_USE_RHS; }
+
+// Will the element-wise product take a block of nr right-hand sides?  Decides the row stride of the vector blocks
+// (solver.cu), so it must agree with ebe_usable once the tables exist: a batch may not fit (the staged rows are addressed
+// with 16-bit byte offsets: order-3 triangles have ~1200 distinct dofs per batch, which rules out 6 columns), so the tables
+// are built here if the element metrics are there.
+bool ebe_serves(Ctx* c, int nr) {
+  if (!ebe_eligible(c) || nr < 1 || nr > EBE_USE_RHS) return false;
+  if (!c->have_ebe && c->have_matrix) ebe_build(c);
+  return c->have_ebe ? c->ebe_occ[nr] > 0 : true;
+}
 
 bool ebe_usable(const Ctx* c, int nr) { return c->have_ebe && nr >= 1 && nr <= EBE_USE_RHS && c->ebe_occ[nr] > 0; }
 
@@ -624,9 +641,10 @@ int ebe_grid(const Ctx* c, int nr) { return (int)std::min<int64_t>(c->ebe_nb, (i
 
 namespace {
 
-template <int NLD>
+template <int NLD, int NG>
 void ebe_build_t(Ctx* c) {
   constexpr int TPB = Batch<NLD>::TPB;
+  constexpr int DIM = (NG == 10) ? 3 : 2;
   cudaStream_t st = c->stream;
   const int64_t nt = c->nt, nb = (nt + TPB - 1) / TPB;
   size_t bytes = 0;
@@ -635,7 +653,7 @@ void ebe_build_t(Ctx* c) {
   uint64_t* codes = scratch<uint64_t>(c, 1, nt);
   int32_t* idx = scratch<int32_t>(c, 2, nt);
   int32_t* tperm = scratch<int32_t>(c, 3, nt);
-  LAUNCH(c, k_tet_morton, grid_for(nt, 256), 256, 0, c->sv.p, c->xyz.p, mesh_bbox(c), nt, code, idx);
+  LAUNCH(c, k_tet_morton<DIM>, grid_for(nt, 256), 256, 0, c->sv.p, c->xyz.p, mesh_bbox(c), nt, code, idx);
   CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, code, codes, idx, tperm, nt, 0, 63, st));
   c->tmp.ensure(bytes, st);
   CK(cub::DeviceRadixSort::SortPairs(c->tmp.p, bytes, code, codes, idx, tperm, nt, 0, 63, st));
@@ -670,23 +688,35 @@ void ebe_build_t(Ctx* c) {
   c->ebe_gm.ensure((size_t)nb * TPB * NG, st);
   LAUNCH(c, (k_ebe_batch<true, NLD>), (unsigned)nb, TPB, 0, sview, tperm, split, color, c->constrained.p, nullptr, nullptr, c->ebe_uoff.p, c->ebe_udof.p,
          c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_ucnt.p, c->ebe_jd.p);
-  LAUNCH(c, k_ebe_gm<TPB>, grid_for(nb * TPB, 256), 256, 0, c->gm.p, tperm, nt, nb, c->ebe_gm.p);
+  LAUNCH(c, (k_ebe_gm<TPB, NG>), grid_for(nb * TPB, 256), 256, 0, c->gm.p, tperm, nt, nb, c->ebe_gm.p);
   c->ebe_nb = nb;
   c->ebe_nld = NLD;
+  c->ebe_ng = NG;
   c->ebe_fast8 = (split > 0 && split <= 8 && umax <= Batch<NLD>::NJ * TPB) ? 1 : 0;
   c->ebe_umax = umax;
   // resident CTAs per SM for every right-hand-side count (the shared-memory row stride of xs depends on it)
   // raised once per (kernel, device) to the opt-in maximum, never to a per-mesh value: other contexts of this GPU launch the
   // same kernel for other meshes (ctx.cuh allow_max_smem)
-  const bool four = NLD == 20 && c->ebe_p3_ctas >= 4;  // order 3: the 128-register build (4 resident CTAs, 240 B of spills)
-  const int dev_max = four ? allow_max_smem(k_spmm_ebe<NLD, 4>, c->device) : allow_max_smem(k_spmm_ebe<NLD>, c->device);
+  // order 3 also has a 128-register build (4 resident CTAs, 240 B of spills): remo_set_option("ebe_p3_ctas", 4)
+  bool four = false;
+  if constexpr (NLD == 20) four = c->ebe_p3_ctas >= 4;
+  int dev_max = 0;
+  if constexpr (NLD == 20) {
+    dev_max = four ? allow_max_smem(k_spmm_ebe<NLD, NG, 4>, c->device) : allow_max_smem(k_spmm_ebe<NLD, NG>, c->device);
+  } else {
+    dev_max = allow_max_smem(k_spmm_ebe<NLD, NG>, c->device);
+  }
   for (int nr = 1; nr <= EBE_MAX_RHS; nr++) {
     const size_t sm = ebe_smem(umax, nr);
     int occ = 0;
     // the kernel keeps byte offsets into xs as 16-bit numbers
     if (sm <= (size_t)dev_max && (size_t)umax * (nr | 1) * 8 < 65536) {
-      if (four) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_ebe<NLD, 4>, TPB, sm));
-      else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_ebe<NLD>, TPB, sm));
+      if constexpr (NLD == 20) {
+        if (four) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_ebe<NLD, NG, 4>, TPB, sm));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_ebe<NLD, NG>, TPB, sm));
+      } else {
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmm_ebe<NLD, NG>, TPB, sm));
+      }
     }
     c->ebe_occ[nr] = occ;  // 0: a batch does not fit (degenerate mesh) -> the SELL / CSR kernels take over
   }
@@ -702,32 +732,37 @@ void ebe_build_t(Ctx* c) {
   c->have_ebe = true;
 }
 
-template <int NLD>
+template <int NLD, int NG>
 void launch_t(Ctx* c, const double* P, int pstride, double* Q, int ks, int nr) {
   cudaStream_t st = c->stream;
   const int xst = nr | 1;
   const int grid = ebe_grid(c, nr);
   static const int pf = [] { const char* e = getenv("REMO_EBE_PREFETCH"); return e ? atoi(e) : 1; }();
   const size_t sm = ebe_smem(c->ebe_umax, nr);
-  if (NLD == 20 && c->ebe_p3_ctas >= 4)
-    k_spmm_ebe<NLD, 4><<<grid, Batch<NLD>::TPB, sm, st>>>((int)c->ebe_nb, c->ebe_uoff.p, c->ebe_udof.p, c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_ucnt.p,
-                                                            c->ebe_jd.p, c->ebe_gm.p, P, pstride, Q, ks, nr, xst, c->ebe_umax, c->ebe_fast8, pf, c->partial.p);
-  else
-    k_spmm_ebe<NLD><<<grid, Batch<NLD>::TPB, sm, st>>>((int)c->ebe_nb, c->ebe_uoff.p, c->ebe_udof.p, c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_ucnt.p, c->ebe_jd.p,
-                                                         c->ebe_gm.p, P, pstride, Q, ks, nr, xst, c->ebe_umax, c->ebe_fast8, pf, c->partial.p);
+  if constexpr (NLD == 20) {
+    if (c->ebe_p3_ctas >= 4) {
+      k_spmm_ebe<NLD, NG, 4><<<grid, Batch<NLD>::TPB, sm, st>>>((int)c->ebe_nb, c->ebe_uoff.p, c->ebe_udof.p, c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_ucnt.p,
+                                                              c->ebe_jd.p, c->ebe_gm.p, P, pstride, Q, ks, nr, xst, c->ebe_umax, c->ebe_fast8, pf, c->partial.p);
+      return;
+    }
+  }
+  k_spmm_ebe<NLD, NG><<<grid, Batch<NLD>::TPB, sm, st>>>((int)c->ebe_nb, c->ebe_uoff.p, c->ebe_udof.p, c->ebe_lidx.p, c->ebe_lpos.p, c->ebe_ucnt.p, c->ebe_jd.p,
+                                                       c->ebe_gm.p, P, pstride, Q, ks, nr, xst, c->ebe_umax, c->ebe_fast8, pf, c->partial.p);
 }
 
 }  // namespace
 
 void ebe_build(Ctx* c) {
-  if (c->order == 3) ebe_build_t<20>(c);
-  else ebe_build_t<10>(c);
+  if (c->dim == 2) ebe_build_t<10, 18>(c);  // order-3 triangles
+  else if (c->order == 3) ebe_build_t<20, 10>(c);
+  else ebe_build_t<10, 10>(c);
 }
 
 void launch_spmm_ebe(Ctx* c, const double* P, int pstride, double* Q, int ks, int nr) {
   CK(cudaMemsetAsync(Q, 0, (size_t)c->ndof * ks * sizeof(double), c->stream));
-  if (c->ebe_nld == 20) launch_t<20>(c, P, pstride, Q, ks, nr);
-  else launch_t<10>(c, P, pstride, Q, ks, nr);
+  if (c->ebe_ng == 18) launch_t<10, 18>(c, P, pstride, Q, ks, nr);
+  else if (c->ebe_nld == 20) launch_t<20, 10>(c, P, pstride, Q, ks, nr);
+  else launch_t<10, 10>(c, P, pstride, Q, ks, nr);
   c->launches += 2;
   CK(cudaGetLastError());
 }

@@ -531,7 +531,10 @@ int vec_grid(Ctx* c, int ks) {
 #define DISPATCH_W(ks, CALL)                      \
   if ((ks) & 1) { constexpr int W = 1; CALL; }    \
   else { constexpr int W = 2; CALL; }
-bool use_sell(const Ctx* c, int nrhs, const double* P) { return c->have_sell && c->pstride >= 2 && (nrhs & 1) == 0 && P == c->P.p; }
+// the SELL kernels want P at the stride sell_pstride picks (a power of two); any other even stride goes to the CSR kernels
+bool use_sell(const Ctx* c, int nrhs, const double* P) {
+  return c->have_sell && c->pstride >= 2 && (nrhs & 1) == 0 && P == c->P.p && c->pstride == sell_pstride(nrhs);
+}
 // element-wise product (ebe.cu): order-2 tets, the PCG's own P block, up to 8 right-hand sides
 bool use_ebe(const Ctx* c, const double* P) { return P == c->P.p && ebe_usable(c, c->nrhs_user); }
 int spmm_grid(Ctx* c, int nrhs) {
@@ -564,7 +567,7 @@ void alloc_solver_state(Ctx* c, int nrhs) {
   CK(cudaMemsetAsync(c->Zv.p, 0, (size_t)c->nv * c->kz * sizeof(double), st));
   // P alone gets a power-of-two row stride when the SELL SpMM gathers it (sell.cu): no gathered row straddles a line.
   // The element-wise product stages whole rows of P once per batch: it takes the plain stride.
-  const bool ebe = ebe_eligible(c) && nrhs <= ebe_max_rhs();
+  const bool ebe = ebe_serves(c, nrhs);
   c->pstride = (!ebe && spmm_variant() >= 5 && nrhs >= 2 && (nrhs & 1) == 0) ? sell_pstride(nrhs) : nrhs;
   c->P.ensure((size_t)c->ndof * c->pstride, st);
   if (c->pstride != nrhs) CK(cudaMemsetAsync(c->P.p, 0, (size_t)c->ndof * c->pstride * sizeof(double), st));
@@ -586,8 +589,8 @@ int spmm_variant() {
 
 // CSR / SELL kernels: even (they gather two right-hand sides per 16-byte load); the extra column of an odd count has
 // b = 0.  Element-wise product (ebe.cu): exactly nrhs -- no dead column in any vector pass.
-int solver_stride(const Ctx* c, int nrhs) {
-  if (ebe_eligible(c) && nrhs <= ebe_max_rhs()) return nrhs;
+int solver_stride(Ctx* c, int nrhs) {
+  if (ebe_serves(c, nrhs)) return nrhs;
   return (nrhs > 1 && spmm_variant() >= 4) ? ((nrhs + 1) & ~1) : nrhs;
 }
 int spmm_blocks(Ctx* c, int ks) { return spmm_grid(c, ks); }

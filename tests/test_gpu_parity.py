@@ -444,11 +444,11 @@ def _check_spmm(ctx, ks, seed=5):
         assert np.max(abs(pq - dots) / (abs(P * ref).sum(0))) <= 1e-13, k
 
 
-@pytest.mark.parametrize("dim,order,ebe", [(3, 1, 1), (3, 2, 1), (3, 2, 0), (3, 3, 1), (3, 3, 0), (2, 2, 1), (2, 3, 1)])
+@pytest.mark.parametrize("dim,order,ebe", [(3, 1, 1), (3, 2, 1), (3, 2, 0), (3, 3, 1), (3, 3, 0), (2, 2, 1), (2, 3, 1), (2, 3, 0)])
 def test_spmm_kernels_against_scipy(ctx, dim, order, ebe):
     """Every SpMM kernel the PCG can pick (CSR one-column, SELL generic for strides 2/4/16/32, SELL streaming for 5..8
-    right-hand sides, and the element-wise product of ebe.cu, which order-2 AND order-3 tets take for up to 6 right-hand sides
-    unless switched off) against the exact product with the oracle-checked CSR matrix: Q = A P on free rows, 0 on constrained
+    right-hand sides, and the element-wise product of ebe.cu, which order-2 / order-3 tets and order-3 triangles take for up to
+    6 right-hand sides unless switched off) against the exact product with the oracle-checked CSR matrix: Q = A P on free rows, 0 on constrained
     rows, and the fused per-column dots p.q."""
     mesh, sigma = (helpers.ball_case() if dim == 3 else helpers.disc_case())[:2]
     ctx.set_option("spmm_ebe", ebe)
@@ -457,7 +457,7 @@ def test_spmm_kernels_against_scipy(ctx, dim, order, ebe):
         ctx.assemble(sigma)
         ctx.set_option("ebe_check", 1)
         _check_spmm(ctx, (1, 2, 3, 4, 5, 6, 7, 8, 9, 16, 17, 32))
-        if dim == 3 and order in (2, 3):
+        if (dim == 3 and order in (2, 3)) or (dim == 2 and order == 3):  # tets of order 2 / 3, axisymmetric triangles of order 3
             ctx.spmm_apply(np.ones((ctx.ndof, 5)))
             assert ctx.spmm_kind() == (2 if ebe else 1), ctx.spmm_kind()  # 2 = element-wise product, 1 = SELL copy
     finally:

@@ -182,7 +182,10 @@ def test_p3_tet_pair_list_matches_tensors():
     gen = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(gen)
     assert gen.check(T=fo.reference_tensors(3, 3)[0]) < 1e-14  # against the oracle's independent derivation of the tensors
+    Tw = fo.reference_tensors(2, 3, weighted=True)[0]              # [k, m, a, b] -> the generator's m = 6 k + pair
+    assert gen.check(T=Tw.reshape(18, Tw.shape[2], Tw.shape[3]), dim=2) < 1e-14
     with tempfile.TemporaryDirectory() as d:
         path = os.path.join(d, "p3.inc")
         gen.emit(path)
+        gen.emit(path, dim=2, name="p3tri_apply", mode="a")
         assert open(path).read() == open(os.path.join(root, "remo3d_b200", "csrc", "ebe_p3_apply.inc")).read()
