@@ -212,3 +212,47 @@ def test_sliver_pass_of_the_half_ball_mesher():
     np.testing.assert_array_equal(a0, a1)
     for z in ez:  # the electrodes are still mesh vertices
         assert np.any((m1["points"][:, 0] == 0) & (m1["points"][:, 1] == 0) & (np.abs(m1["points"][:, 2] - z) < 1e-12))
+
+
+def test_3d_mesh_carries_the_material_interfaces():
+    """`meshgen.Interfaces` (3D meshes of `Model`, `mesh_options["conforming"]`): lattice points near the borehole wall, a dipping
+    layer plane or an invasion cylinder are projected onto it, so almost no tet straddles an interface, the mud column has its
+    volume inside the resolved window, and the mesh stays a valid triangulation of the half-ball."""
+    from remo3d_b200 import meshgen
+
+    ez = np.array([-1.0, -0.5, 0.0, 0.4])
+    rb, rinv, dip = 0.11, 0.4, np.deg2rad(20.0)
+    tops = [-0.7, 0.9]
+    itf = meshgen.Interfaces(rb, tops, dip, [None, rinv, None])
+    material = meshgen.layered_material(tops, dip_rad=dip, borehole_radius=rb, invasion=[None, rinv, None])
+    kw = dict(h_electrode=0.03, h_axis=0.08, grading=0.35, seed=0)
+    plain = meshgen.half_ball_mesh(20.0, ez, material=material, **kw)
+    conf = meshgen.half_ball_mesh(20.0, ez, material=material, interfaces=itf, h_borehole=0.15, r_strip=rinv, g_borehole=0.8,
+                                  borehole_window=3.0, g_window=0.15, **kw)
+
+    def stats(m):
+        p, e = m["points"], m["elems"]
+        x = p[e]
+        vol = np.linalg.det(x[:, 1:] - x[:, :1]) / 6.0
+        assert (vol > 0).all()
+        assert abs(vol.sum() - 2.0 / 3.0 * np.pi * 20.0 ** 3) < 2e-2 * 2.0 / 3.0 * np.pi * 20.0 ** 3
+        rho = np.hypot(p[:, 0], p[:, 1])
+        near = np.abs(x[:, :, 2]).max(axis=1) < 2.0  # tets inside the resolved part of the column
+        side = np.sign(np.round(rho[e] - rb, 9))      # -1 inside the borehole, 0 on the wall, +1 outside
+        straddle = near & (side.min(axis=1) < 0) & (side.max(axis=1) > 0)
+        touch = near & (np.abs(rho[e] - rb).min(axis=1) < 0.05)
+        mud = vol[(m["mat"] == 0) & near].sum()
+        return straddle.sum() / max(1, touch.sum()), mud, int((np.abs(rho - rb) < 1e-9).sum())
+
+    f_plain, mud_plain, on_plain = stats(plain)
+    f_conf, mud_conf, on_conf = stats(conf)
+    exact = 0.5 * np.pi * rb ** 2 * 4.0  # half column, |z| < 2
+    print("tets straddling the wall / tets near it: plain %.3f, with interfaces %.3f; mud volume %.4f / %.4f (exact %.4f); wall vertices %d / %d"
+          % (f_plain, f_conf, mud_plain, mud_conf, exact, on_plain, on_conf))
+    assert on_plain == 0 and on_conf > 200                       # the wall is sampled by mesh vertices
+    assert f_conf < 0.25 * f_plain and f_conf < 0.08               # (almost) no tet crosses it any more
+    assert abs(mud_conf - exact) < 0.15 * exact                    # and the column has its volume
+    # every electrode is still a vertex
+    axis = conf["points"][(conf["points"][:, 0] == 0.0) & (conf["points"][:, 1] == 0.0), 2]
+    for z in ez:
+        assert np.min(np.abs(axis - z)) < 1e-12
