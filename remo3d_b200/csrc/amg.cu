@@ -20,6 +20,8 @@
 //     Prolongation piecewise constant, the coarsest level (<= 256 rows) is inverted densely.  Smoother: l1-Jacobi
 //     (always a contraction), symmetric cycle, coarse correction over-weighted by 1.5 (plain aggregation
 //     under-corrects) -> M is SPD and plain PCG applies.
+//   * round 2: the cycle itself runs in fp32 (values, l1 weights and work blocks of every level; level 0 reads the PCG's fp64
+//     residual and writes its fp64 z inside the sweeps) around the fp64 PCG -- remo_set_option("amg_fp32", 0) restores fp64.
 // Everything works on row-major n x nrhs blocks, like the PCG.
 #include <cooperative_groups.h>
 #include <cub/cub.cuh>

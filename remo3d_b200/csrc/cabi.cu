@@ -204,7 +204,7 @@ int remo_matrix_get(void* vctx, int64_t* rowptr, int32_t* col, double* val) {
   return guarded(vctx, [&](Ctx* c) {
     if (!c->have_space) FAIL(REMO_ERR_STATE, "remo_matrix_get: no space");
     if (val && !c->have_matrix) FAIL(REMO_ERR_STATE, "remo_matrix_get: matrix not assembled");
-    pattern_build(c);            // lazy: the PCG path of order-2 tets never builds the CSR matrix
+    pattern_build(c);            // lazy: the PCG path of tets and order-3 triangles (element-wise product) never builds the CSR matrix
     if (val) ensure_values(c);
     cudaStream_t st = c->stream;
     if (rowptr) CK(cudaMemcpyAsync(rowptr, c->rowptr.p, (c->ndof + 1) * sizeof(int64_t), cudaMemcpyDefault, st));

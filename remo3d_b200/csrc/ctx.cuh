@@ -117,7 +117,7 @@ struct Ctx {
   int64_t sell_chunks = 0, sell_slots = 0;
   bool have_sell = false;
 
-  // ---- element-wise product for order-2 tets (ebe.cu): batches of 256 Morton-ordered tets
+  // ---- element-wise product (ebe.cu): batches of 256 (order-2 tets, order-3 triangles) or 128 (order-3 tets) Morton-ordered elements
   DBuf<int64_t> ebe_uoff;     // nb+1: first distinct dof of every batch
   DBuf<int32_t> ebe_udof;     // distinct dofs of every batch, bit 31 = constrained
   DBuf<uint16_t> ebe_lidx;    // nb x 10 x 256: (slot, tet) -> position in the batch's dof list

@@ -535,7 +535,7 @@ int vec_grid(Ctx* c, int ks) {
 bool use_sell(const Ctx* c, int nrhs, const double* P) {
   return c->have_sell && c->pstride >= 2 && (nrhs & 1) == 0 && P == c->P.p && c->pstride == sell_pstride(nrhs);
 }
-// element-wise product (ebe.cu): order-2 tets, the PCG's own P block, up to 8 right-hand sides
+// element-wise product (ebe.cu): order-2 / order-3 tets and order-3 triangles, the PCG's own P block, up to 6 right-hand sides
 bool use_ebe(const Ctx* c, const double* P) { return P == c->P.p && ebe_usable(c, c->nrhs_user); }
 int spmm_grid(Ctx* c, int nrhs) {
   if (use_ebe(c, c->P.p)) return ebe_grid(c, c->nrhs_user);
@@ -672,7 +672,7 @@ void precond_setup(Ctx* c, int kind) {
   c->dinv.ensure(c->ndof, c->stream);
   diag_from_elements(c, c->dinv.p);
   if (kind == REMO_PRECOND_MULTIGRID) amg_setup(c);
-  // order-2 tets: the element-wise product needs no copy of the matrix at all; the CSR values and the SELL copy are made
+  // element-wise path (ebe_eligible): the product needs no copy of the matrix at all; the CSR values and the SELL copy are made
   // on demand (spmm_prepare) if a block wider than ebe.cu takes shows up
   if (ebe_eligible(c)) { if (!c->have_ebe) ebe_build(c); }
   else {
