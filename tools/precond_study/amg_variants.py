@@ -149,6 +149,9 @@ def run(size, names):
         "greedy_sa_s2": dict(b=dict(kind="greedy", theta=0.08, smooth_P=True), c=dict(sweeps=2, alpha=1.0)),
         "pair3": dict(b=dict(kind="pair", passes=3), c=dict(sweeps=1, alpha=1.5)),
         "pair2": dict(b=dict(kind="pair", passes=2), c=dict(sweeps=1, alpha=1.5)),
+        "pair3_W": dict(b=dict(kind="pair", passes=3), c=dict(sweeps=1, alpha=1.5, gamma=2)),
+        "pair3_W_a1": dict(b=dict(kind="pair", passes=3), c=dict(sweeps=1, alpha=1.0, gamma=2)),
+        "pair3_s2": dict(b=dict(kind="pair", passes=3), c=dict(sweeps=2, alpha=1.5)),
         "pair3_sa": dict(b=dict(kind="pair", passes=3, smooth_P=True), c=dict(sweeps=1, alpha=1.0)),
         "pair2_sa": dict(b=dict(kind="pair", passes=2, smooth_P=True), c=dict(sweeps=1, alpha=1.0)),
         "mort_sa": dict(b=dict(kind="morton", smooth_P=True), c=dict(sweeps=1, alpha=1.0)),
